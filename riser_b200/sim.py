@@ -1,0 +1,82 @@
+"""Synthetic stand-in for the MinKNOW / ReadUntil client (riser/client.py).
+
+The reference's ``Client`` wraps the third-party ``read_until`` package, which is
+out of scope and unavailable offline; the north star says it is "exercised
+against synthetic signal".  ``SimClient`` offers the same methods
+``SequencerControl`` calls (riser/client.py:33-62, riser/control.py:12,25,31,33,
+100,106,119,127,131) and reproduces the AccumulatingCache semantics
+(riser/client.py:29-31,44): every poll returns, per channel, the WHOLE prefix of
+the current read so far, and the prefix grows by ``chunk`` samples per poll.
+"""
+import numpy as np
+
+
+class SimRead:
+    """What ``get_read_chunks`` yields: ``.id``, ``.raw_data`` (bytes), ``.number``."""
+    __slots__ = ("id", "number", "raw_data")
+
+    def __init__(self, read_id, number, raw_data):
+        self.id = read_id
+        self.number = number
+        self.raw_data = raw_data
+
+
+class SimClient:
+    signal_dtype = np.int16
+
+    def __init__(self, reads, chunk, n_polls, first_len=None, with_number=True):
+        """reads: list of (read_id, int16 full signal); channel c (1-based) carries
+        reads[c-1].  Each poll exposes ``first_len + k*chunk`` samples (capped at the
+        read's length).  After ``n_polls`` polls ``is_running`` turns False."""
+        self.reads = reads
+        self.chunk = int(chunk)
+        self.first_len = int(first_len if first_len is not None else chunk)
+        self.n_polls = int(n_polls)
+        self.poll = 0
+        self.done = set()          # (channel, id-or-number) passed to stop_receiving
+        self.unblocked = []        # every (channel, id) ever passed to unblock
+        self.finished = []
+        self.messages = []
+        self.running = False
+        self.with_number = with_number
+
+    # riser/client.py:33-41
+    def start_streaming_reads(self):
+        self.running = True
+
+    def is_running(self):
+        return self.running and self.poll < self.n_polls
+
+    # riser/client.py:43-47
+    def get_read_batch(self):
+        n = self.first_len + self.poll * self.chunk
+        self.poll += 1
+        batch = []
+        for c, (rid, sig) in enumerate(self.reads, start=1):
+            key = (c, c if self.with_number else rid)
+            if key in self.done:
+                continue
+            batch.append((c, SimRead(rid, c if self.with_number else None, sig[:n].tobytes())))
+        if not self.with_number:
+            for _, r in batch:
+                del r.number
+        return batch
+
+    def get_raw_signal(self, read):
+        return np.frombuffer(read.raw_data, self.signal_dtype)
+
+    # riser/client.py:49-56
+    def reject_reads(self, reads, unblock_duration):
+        if reads:
+            self.unblocked.extend(reads)
+
+    def finish_processing_reads(self, reads):
+        if reads:
+            self.finished.extend(reads)
+            self.done.update(reads)
+
+    def reset(self):
+        self.running = False
+
+    def send_warning(self, message):
+        self.messages.append(message)
