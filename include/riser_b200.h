@@ -1,0 +1,152 @@
+/*
+ * riser_b200 -- C ABI of the B200-native RISER read-classification hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers + sizes, no torch
+ * types) over hand-written sm_100a kernels.  The reference (comprna/riser) has no
+ * FFI of its own -- its hot path is three Python objects -- so each entry point
+ * below cites the reference function it replaces (paths relative to the reference
+ * checkout).  The Python host side (riser_b200/{preprocess,model,control}.py)
+ * mirrors the reference's Kit / SignalProcessor / Model / SequencerControl call
+ * surface and reaches these functions through ctypes (riser_b200/_lib.py);
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every launch function takes the cudaStream_t to run on, never synchronises
+ *     and never allocates: the caller owns all buffers (capturable in CUDA graphs);
+ *   - return value 0 = ok, otherwise a RISER_E* code; riser_last_error() returns a
+ *     thread-local message; no C++ exception crosses the boundary;
+ *   - there is NO CPU fallback: without an sm_100 device the calls return
+ *     RISER_ECUDA.
+ */
+#ifndef RISER_B200_H
+#define RISER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* riser_stream_t; /* == cudaStream_t */
+
+enum {
+  RISER_OK = 0,
+  RISER_EINVAL = 1, /* bad argument (null pointer, size out of range, misalignment) */
+  RISER_ECUDA = 2,  /* CUDA runtime / driver error, or no sm_100 device            */
+  RISER_ENOMEM = 3, /* workspace too small                                         */
+};
+
+/* Decision codes written by riser_decide (riser/control.py:75-82; 4 = the two
+ * `continue` branches at control.py:50,56). */
+enum {
+  RISER_TRY_AGAIN = 0,
+  RISER_ACCEPT = 1,
+  RISER_REJECT = 2,
+  RISER_NO_DECISION = 3,
+  RISER_SKIPPED = 4,
+};
+
+/* mode argument of riser_decide (riser/riser.py:91-95, control.py:76,78) */
+enum { RISER_MODE_ENRICH = 0, RISER_MODE_DEPLETE = 1 };
+
+/* Arithmetic of the convolution stack (layers 1..n-1; layer 0 and the head are
+ * always fp32).  Operands are fp16 (10-bit mantissa, the same as tf32, at twice
+ * the tensor rate); accumulation is fp32 in TMEM.
+ *   F16    : one tcgen05 pass, weights rounded to fp16.
+ *   F16_W2 : two passes, weights split hi + lo fp16 (weights exact to ~22 bits);
+ *            only the activation rounding remains.                              */
+enum { RISER_PREC_F16 = 0, RISER_PREC_F16_W2 = 1 };
+
+int riser_version(void);
+const char* riser_last_error(void);
+
+/* Device properties the host side needs: fills sm_count, cc_major, cc_minor. */
+int riser_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ preprocessing */
+
+/* Maximum window length riser_normalise accepts (samples staged in shared memory). */
+int riser_normalise_max_len(void);
+
+/* Replaces SignalProcessor.mad_normalise + _calculate_mad + _normalise +
+ * _smooth_outliers + _clip_if_outlier (riser/preprocess.py:108-147), batched over
+ * ragged windows.  Read b's window is sig[off[b] + start[b] .. + len[b]).
+ * Exact integer selection of median and MAD, float64 normalise and sequential
+ * outlier smoothing exactly as the reference, result rounded to fp32 (the cast
+ * riser/model.py:25 applies) into out[b * ld_out + i], i < len[b].  Elements
+ * i >= len[b] of the row are not written.  len[b] == 0 writes nothing.
+ * mad == 0 writes zeros (preprocess.py:122-124).
+ * out must be 16-byte aligned and ld_out a multiple of 4.
+ * med2_mad4 (optional, may be NULL): int32 [B,2] = {2*median, 4*MAD} (exact).  */
+int riser_normalise(const int16_t* sig, const int64_t* off, const int32_t* start,
+                    const int32_t* len, int B, int max_len, float* out, int64_t ld_out,
+                    int32_t* med2_mad4, riser_stream_t stream);
+
+/* Same for fp32 input (the pA-scaled path of riser/retrain/preprocess.py:36-44):
+ * NOT implemented in this round; declared so the binding is stable.            */
+
+/* Replaces SignalProcessor.get_polyA_end (riser/preprocess.py:42-79), batched.
+ * Read b is sig[off[b] .. off[b] + n[b]).  polya_end[b] = the returned window
+ * start index, or -1 for None.  Window statistics are exact integers; the
+ * mean-change test is evaluated in float64 in the reference's operation order.
+ * stats (optional, may be NULL): int32 [B, max_windows, 3] = {sum, 2*median,
+ * 4*MAD} per 500-sample window.                                                */
+int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, int B,
+                    int32_t* polya_end, int32_t* stats, int max_windows,
+                    riser_stream_t stream);
+
+/* ------------------------------------------------------------------ network */
+
+typedef struct riser_model riser_model; /* packed weights of one ConvNet on one device */
+typedef struct riser_plan riser_plan;   /* launch plan for one (batch, max length) shape */
+
+/* Replaces Model.__init__'s ConvNet(config.cnn) + load_state_dict
+ * (riser/model.py:18-20, riser/nets/cnn.py:8-41,52-65; depth 1, 'gap_fc' head,
+ * 2 classes, kernel 3 -- the only shape the shipped configs use,
+ * riser/model/\*.yaml:6-12).  conv_w_host[i] is the fp32 [channels[i], cin_i, 3]
+ * weight of layers.{i}.0 (cin_0 = 1, cin_i = channels[i-1]); conv_b_host[i] its
+ * bias; fc_w_host [2, channels[n-1]], fc_b_host [2] the classifier.2 tensors.
+ * Packs them on the host into the tap-major, channel-padded fp16 layout the
+ * tcgen05 kernel reads and uploads them to `device`.                           */
+int riser_model_create(riser_model** out, int n_layers, const int* channels,
+                       const float* const* conv_w_host, const float* const* conv_b_host,
+                       const float* fc_w_host, const float* fc_b_host, int precision,
+                       int device);
+int riser_model_destroy(riser_model* m);
+
+/* Bytes of activation workspace a plan for (B reads, longest window max_len) needs. */
+size_t riser_workspace_bytes(const riser_model* m, int B, int max_len);
+
+/* Builds the TMA tensor maps and per-layer launch geometry for (B, max_len) over
+ * the caller's workspace (256-byte aligned, >= riser_workspace_bytes; it is
+ * zeroed once here, asynchronously on `stream`).                               */
+int riser_plan_create(riser_plan** out, const riser_model* m, int B, int max_len,
+                      void* workspace, size_t workspace_bytes, riser_stream_t stream);
+int riser_plan_destroy(riser_plan* p);
+
+/* Replaces Model.classify (riser/model.py:22-28) and ConvNet.forward
+ * (riser/nets/cnn.py:43-50), batched over ragged reads: x is the normalised
+ * signal, fp32 [B, ld_x], read b valid for len[b] samples (4096 <= len[b] <=
+ * max_len).  Per-layer length masks (L_{i+1} = floor(L_i / 2)) make every read's
+ * result equal to classifying it alone.  probs [B, 2] = softmax(logits) =
+ * (p_off_target, p_on_target).  A read with len[b] < 4096 gets NaN (the
+ * reference raises in max_pool1d for such input).
+ * feat (optional, may be NULL): fp32 [B, channels[n-1]] pooled features.       */
+int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len,
+                  float* probs, float* feat, riser_stream_t stream);
+
+/* Number of kernels one riser_forward launches (for gpu_launches accounting). */
+int riser_forward_launches(const riser_plan* p);
+
+/* Replaces the decision rule of riser/control.py:75-82 for M models:
+ * probs [M, B, 2]; len [B] = post-trim window length, 0 = read was skipped
+ * (control.py:50,56) -> RISER_SKIPPED.  Strict '>' against thr in fp32.        */
+int riser_decide(const float* probs, const int32_t* len, int B, int M, float thr, int mode,
+                 int max_len, uint8_t* decision, riser_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RISER_B200_H */

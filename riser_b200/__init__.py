@@ -1,0 +1,6 @@
+"""riser_b200 -- B200-native implementation of the RISER read-classification hot
+path (trim -> normalise -> 1-D CNN -> decision) behind the reference's
+Kit / SignalProcessor / Model / SequencerControl call surface."""
+from .preprocess import Kit, SignalProcessor, RaggedBatch      # noqa: F401
+
+__all__ = ["Kit", "SignalProcessor", "RaggedBatch"]

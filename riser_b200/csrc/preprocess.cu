@@ -1,0 +1,471 @@
+// Preprocessing kernels of the RISER hot path for sm_100a:
+//   riser_normalise  -- fused median / MAD / normalise / outlier smoothing over ragged
+//                       int16 windows (riser/preprocess.py:108-147)
+//   riser_polya_end  -- 500-sample window statistics + the 2-state poly(A) scan
+//                       (riser/preprocess.py:42-79)
+// Both are HBM-bound byte/integer work: one CTA per read, the window staged once in
+// shared memory with 16-byte coalesced loads, exact integer selection (histogram radix
+// select for whole windows, warp-shuffle bit-descent select for 500-sample windows),
+// float64 arithmetic in the reference's operation order, fp32 results written with
+// 16-byte stores.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace riser {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kBins = 2048;             // first-pass histogram bins
+constexpr int kBinsPerThread = kBins / kThreads;
+constexpr int kSubBins = 128;           // refinement pass (shift <= 7)
+constexpr int kMaxLen = 98304;          // samples staged in smem (192 KB)
+
+constexpr double kOutlierLimit = 3.5;   // riser/preprocess.py:6
+constexpr double kScalingFactor = 1.4826;  // riser/preprocess.py:7
+
+struct SelectScratch {
+  uint32_t hist[kBins];
+  uint32_t sub[kSubBins];
+  uint32_t warp_sums[kWarps];
+  uint32_t res[4];      // bin1, before1, bin2, before2
+  uint32_t refined;
+  int32_t red[2 * kWarps];
+};
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += n;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t w = 0; w < warp; ++w) base += warp_sums[w];
+  __syncthreads();
+  return base + inc - v;
+}
+
+// Exact order statistics k1 <= k2 (0-based) of the n keys key(0..n-1), all <= maxkey.
+// Pass A: histogram of key >> shift with shift chosen so that it fits kBins; block scan
+// locates the bins holding the two ranks.  Pass B (only when shift > 0): histogram of the
+// low bits inside the located bin.  Block-uniform control flow; all threads get r1, r2.
+template <class KeyFn>
+__device__ void select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32_t k2,
+                           SelectScratch& s, uint32_t& r1, uint32_t& r2) {
+  const int tid = threadIdx.x;
+  int shift = 0;
+  while ((maxkey >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
+  for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kThreads) atomicAdd(&s.hist[key(i) >> shift], 1u);
+  __syncthreads();
+  uint32_t c[kBinsPerThread];
+  uint32_t local = 0;
+#pragma unroll
+  for (int j = 0; j < kBinsPerThread; ++j) {
+    c[j] = s.hist[tid * kBinsPerThread + j];
+    local += c[j];
+  }
+  const uint32_t ex = block_exclusive_scan(local, s.warp_sums);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t k = which ? k2 : k1;
+    if (k >= ex && k < ex + local) {
+      uint32_t run = ex;
+#pragma unroll
+      for (int j = 0; j < kBinsPerThread; ++j) {
+        if (k >= run && k < run + c[j]) {
+          s.res[2 * which] = tid * kBinsPerThread + j;
+          s.res[2 * which + 1] = run;
+        }
+        run += c[j];
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t bin1 = s.res[0], before1 = s.res[1], bin2 = s.res[2], before2 = s.res[3];
+  if (shift == 0) {
+    r1 = bin1;
+    r2 = bin2;
+    __syncthreads();
+    return;
+  }
+  const uint32_t mask = (1u << shift) - 1u;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t bin = which ? bin2 : bin1;
+    const uint32_t kk = which ? (k2 - before2) : (k1 - before1);
+    __syncthreads();
+    for (int i = tid; i < kSubBins; i += kThreads) s.sub[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) {
+      const uint32_t kx = key(i);
+      if ((kx >> shift) == bin) atomicAdd(&s.sub[kx & mask], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t run = 0, found = 0;
+      for (uint32_t j = 0; j <= mask; ++j) {
+        if (kk >= run && kk < run + s.sub[j]) found = j;
+        run += s.sub[j];
+      }
+      s.refined = (bin << shift) | found;
+    }
+    __syncthreads();
+    if (which) r2 = s.refined; else r1 = s.refined;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double norm_value(int x, double median, double denom) {
+  // (x - median) / (1.4826 * mad), riser/preprocess.py:122-125, IEEE round-to-nearest
+  return __ddiv_rn(__dsub_rn(static_cast<double>(x), median), denom);
+}
+__device__ __forceinline__ double clip_outlier(double v) {
+  // riser/preprocess.py:141-147
+  if (v > kOutlierLimit) return kOutlierLimit;
+  if (v < -kOutlierLimit) return -kOutlierLimit;
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
+                 const int32_t* __restrict__ start, const int32_t* __restrict__ len, int B,
+                 float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ med2_mad4) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelectScratch& s = *reinterpret_cast<SelectScratch*>(smem_raw);
+  int16_t* stage = reinterpret_cast<int16_t*>(smem_raw + ((sizeof(SelectScratch) + 15) & ~size_t(15)));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int n = len[b];
+    if (n <= 0) continue;
+    const int16_t* g = sig + off[b] + (start ? start[b] : 0);
+    float* o = out + static_cast<int64_t>(b) * ld_out;
+
+    // ---- stage the window in smem at the same 16-byte phase as in global memory
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 1) & 7);
+    const int16_t* x = stage + a;                    // x[i] == g[i]
+    const int n_chunks = (a + n + 7) >> 3;
+    const uint4* g4 = reinterpret_cast<const uint4*>(g - a);
+    uint4* s4 = reinterpret_cast<uint4*>(stage);
+    int vmin = 32767, vmax = -32768;
+    for (int c = tid; c < n_chunks; c += kThreads) {
+      const int lo = 8 * c - a;
+      if (lo >= 0 && lo + 8 <= n) {
+        const uint4 v = __ldg(g4 + c);
+        s4[c] = v;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e0 = static_cast<int16_t>(w[j] & 0xffff);
+          const int e1 = static_cast<int16_t>(w[j] >> 16);
+          vmin = min(vmin, min(e0, e1));
+          vmax = max(vmax, max(e0, e1));
+        }
+      } else {
+        for (int i = max(lo, 0); i < min(lo + 8, n); ++i) {
+          const int e = g[i];
+          stage[a + i] = static_cast<int16_t>(e);
+          vmin = min(vmin, e);
+          vmax = max(vmax, e);
+        }
+      }
+    }
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if (lane == 0) {
+      s.red[warp] = vmin;
+      s.red[kWarps + warp] = vmax;
+    }
+    __syncthreads();
+    vmin = s.red[0];
+    vmax = s.red[kWarps];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) {
+      vmin = min(vmin, s.red[w]);
+      vmax = max(vmax, s.red[kWarps + w]);
+    }
+
+    // ---- median: mean of the two middle order statistics -> med2 = 2 * median (exact)
+    const uint32_t k1 = static_cast<uint32_t>((n - 1) >> 1), k2 = static_cast<uint32_t>(n >> 1);
+    uint32_t r1, r2;
+    select_two([&](int i) { return static_cast<uint32_t>(x[i] - vmin); }, n,
+               static_cast<uint32_t>(vmax - vmin), k1, k2, s, r1, r2);
+    const int med2 = 2 * vmin + static_cast<int>(r1 + r2);
+
+    // ---- MAD on keys d = |2x - med2| = 2|x - median| -> mad4 = 4 * MAD (exact)
+    const uint32_t dmax = static_cast<uint32_t>(max(abs(2 * vmin - med2), abs(2 * vmax - med2)));
+    select_two([&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)); }, n, dmax, k1, k2,
+               s, r1, r2);
+    const uint32_t mad4 = r1 + r2;
+    if (med2_mad4 && tid == 0) {
+      med2_mad4[2 * b] = med2;
+      med2_mad4[2 * b + 1] = static_cast<int32_t>(mad4);
+    }
+
+    const int n_groups = (n + 3) >> 2;
+    if (mad4 == 0) {   // riser/preprocess.py:123-124
+      for (int gidx = tid; gidx < n_groups; gidx += kThreads) {
+        const int i0 = 4 * gidx;
+        if (i0 + 4 <= n) {
+          *reinterpret_cast<float4*>(o + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int i = i0; i < n; ++i) o[i] = 0.f;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+
+    const double median = static_cast<double>(med2) * 0.5;
+    const double mad = static_cast<double>(mad4) * 0.25;
+    const double denom = __dmul_rn(kScalingFactor, mad);
+
+    // ---- outlier threshold in the integer key domain: |z| > 3.5  <=>  d > dthr, where
+    //      z = fl((d/2) / denom) is monotone in d.  Found once per read with exact divides.
+    if (tid == 0) {
+      auto zval = [&](uint32_t d) { return __ddiv_rn(static_cast<double>(d) * 0.5, denom); };
+      uint32_t d0 = static_cast<uint32_t>(__dmul_rn(7.0, denom));
+      while (zval(d0 + 1) <= kOutlierLimit) ++d0;
+      while (d0 > 0 && zval(d0) > kOutlierLimit) --d0;
+      s.refined = d0;
+    }
+    __syncthreads();
+    const uint32_t dthr = s.refined;
+    auto flagged = [&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)) > dthr; };
+
+    // ---- normalise + smooth, 4 samples per thread-iteration, 16-byte stores
+    for (int gidx = tid; gidx < n_groups; gidx += kThreads) {
+      const int i0 = 4 * gidx;
+      const int cnt = min(4, n - i0);
+      bool f[4];
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f[e] = (e < cnt) && flagged(i0 + e);
+        any |= f[e];
+      }
+      if (!any && cnt == 4) {
+        float4 v;
+        v.x = static_cast<float>(norm_value(x[i0], median, denom));
+        v.y = static_cast<float>(norm_value(x[i0 + 1], median, denom));
+        v.z = static_cast<float>(norm_value(x[i0 + 2], median, denom));
+        v.w = static_cast<float>(norm_value(x[i0 + 3], median, denom));
+        *reinterpret_cast<float4*>(o + i0) = v;
+        continue;
+      }
+      for (int e = 0; e < cnt; ++e) {
+        const int i = i0 + e;
+        if (!f[e]) {
+          o[i] = static_cast<float>(norm_value(x[i], median, denom));
+          continue;
+        }
+        const bool prev_flag = (i > 0) && (e > 0 ? f[e - 1] : flagged(i - 1));
+        if (prev_flag) continue;   // inside a run: the thread at the run start walks it
+        // Walk the run of consecutive outliers starting at i, sequentially, exactly as
+        // riser/preprocess.py:130-138: arr[j-1] is already updated, arr[j+1] is still raw.
+        double prev = (i > 0) ? norm_value(x[i - 1], median, denom) : 0.0;
+        for (int j = i; j < n && flagged(j); ++j) {
+          double nv;
+          if (j == 0) {
+            nv = (n > 1) ? norm_value(x[1], median, denom) : norm_value(x[0], median, denom);
+          } else if (j == n - 1) {
+            nv = prev;
+          } else {
+            nv = clip_outlier(__dmul_rn(__dadd_rn(prev, norm_value(x[j + 1], median, denom)), 0.5));
+          }
+          o[j] = static_cast<float>(nv);
+          prev = nv;
+        }
+      }
+    }
+    __syncthreads();   // stage / scratch are reused by the next read
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// poly(A) end detection.  One CTA per read; one warp per 500-sample window.
+
+constexpr int kRes = 500;               // _TRIM_RESOLUTION, riser/preprocess.py:10
+constexpr int kPerLane = (kRes + 31) / 32;   // 16
+constexpr int kMaxWindows = 2048;
+
+// rank-k (0-based) key among this warp's valid keys, bit-serial radix descent with
+// warp-wide counts (REDUX); keys < 2^nbits.
+__device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[kPerLane], const bool (&valid)[kPerLane],
+                                                int nbits, uint32_t k) {
+  uint32_t prefix = 0;
+  for (int bit = nbits - 1; bit >= 0; --bit) {
+    const uint32_t hi_mask = ~((2u << bit) - 1u);
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j)
+      cnt += (valid[j] && ((key[j] & hi_mask) == prefix) && !((key[j] >> bit) & 1u)) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (k >= static_cast<uint32_t>(cnt)) {
+      k -= cnt;
+      prefix |= 1u << bit;
+    }
+  }
+  return prefix;
+}
+
+// the two middle order statistics (ranks 249 and 250 of 500) -> their sum
+__device__ __forceinline__ uint32_t warp_mid_sum(const uint32_t (&key)[kPerLane], const bool (&valid)[kPerLane],
+                                                 int nbits) {
+  const uint32_t v1 = warp_select(key, valid, nbits, kRes / 2 - 1);
+  int le = 0;
+  uint32_t next = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    if (valid[j]) {
+      le += key[j] <= v1 ? 1 : 0;
+      if (key[j] > v1) next = min(next, key[j]);
+    }
+  }
+  le = __reduce_add_sync(0xffffffffu, le);
+  next = __reduce_min_sync(0xffffffffu, next);
+  const uint32_t v2 = (le > kRes / 2) ? v1 : next;
+  return v1 + v2;
+}
+
+__global__ void __launch_bounds__(kThreads)
+polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
+             const int32_t* __restrict__ nsamp, int B, int32_t* __restrict__ polya_end,
+             int32_t* __restrict__ stats, int max_windows) {
+  __shared__ int32_t w_sum[kMaxWindows];
+  __shared__ int32_t w_mad4[kMaxWindows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int n = nsamp[b];
+    const int16_t* g = sig + off[b];
+    const int nw = min(n / kRes, kMaxWindows);
+    for (int w = warp; w < nw; w += kWarps) {
+      const int16_t* wp = g + w * kRes;
+      uint32_t key[kPerLane];
+      bool valid[kPerLane];
+      int sum = 0;
+#pragma unroll
+      for (int j = 0; j < kPerLane; ++j) {
+        const int idx = j * 32 + lane;
+        valid[j] = idx < kRes;
+        const int v = valid[j] ? static_cast<int>(wp[idx]) : 0;
+        sum += v;
+        key[j] = static_cast<uint32_t>(v + 32768);
+      }
+      sum = __reduce_add_sync(0xffffffffu, sum);
+      const int med2 = static_cast<int>(warp_mid_sum(key, valid, 16)) - 65536;   // 2 * median
+#pragma unroll
+      for (int j = 0; j < kPerLane; ++j)
+        key[j] = static_cast<uint32_t>(abs(2 * (static_cast<int>(key[j]) - 32768) - med2));
+      const uint32_t mad4 = warp_mid_sum(key, valid, 18);                         // 4 * MAD
+      if (lane == 0) {
+        w_sum[w] = sum;
+        w_mad4[w] = static_cast<int32_t>(mad4);
+        if (stats && w < max_windows) {
+          int32_t* st = stats + (static_cast<int64_t>(b) * max_windows + w) * 3;
+          st[0] = sum;
+          st[1] = med2;
+          st[2] = static_cast<int32_t>(mad4);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // riser/preprocess.py:45-72.  0 doubles as "unset" exactly like Python truthiness.
+      int pstart = 0, pend = 0;
+      for (int w = 0; w < nw; ++w) {
+        const int i = w * kRes;
+        const double mean = __ddiv_rn(static_cast<double>(w_sum[w]), static_cast<double>(kRes));
+        double rolling = mean;
+        if (i > 2 * kRes)
+          rolling = __ddiv_rn(static_cast<double>(w_sum[w - 2] + w_sum[w - 1]),
+                              static_cast<double>(2 * kRes));
+        const double change = __dmul_rn(__ddiv_rn(__dsub_rn(mean, rolling), rolling), 100.0);
+        const double mad = static_cast<double>(w_mad4[w]) * 0.25;
+        if (pstart == 0 && change > 20.0 && mad <= 20.0) pstart = i;
+        if (pstart != 0 && pend == 0 && mad > 20.0) pend = i;
+      }
+      polya_end[b] = pend ? pend : -1;
+    }
+    __syncthreads();
+  }
+}
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+}  // namespace
+}  // namespace riser
+
+using namespace riser;
+
+extern "C" int riser_version(void) { return 100; }
+extern "C" const char* riser_last_error(void) { return err_buf(); }
+
+extern "C" int riser_device_info(int device, int* sm, int* major, int* minor) {
+  RISER_REQUIRE(sm && major && minor, "riser_device_info: null output pointer");
+  RISER_CUDA_TRY(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, device));
+  RISER_CUDA_TRY(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, device));
+  RISER_CUDA_TRY(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, device));
+  return RISER_OK;
+}
+
+extern "C" int riser_normalise_max_len(void) { return kMaxLen; }
+
+extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int32_t* start,
+                               const int32_t* len, int B, int max_len, float* out, int64_t ld_out,
+                               int32_t* med2_mad4, riser_stream_t stream) {
+  RISER_REQUIRE(B >= 0, "riser_normalise: B < 0");
+  if (B == 0) return RISER_OK;
+  RISER_REQUIRE(sig && off && len && out, "riser_normalise: null pointer");
+  RISER_REQUIRE(max_len > 0 && max_len <= kMaxLen, "riser_normalise: max_len %d outside (0, %d]",
+                max_len, kMaxLen);
+  RISER_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ld_out & 3) == 0 && ld_out >= max_len,
+                "riser_normalise: out must be 16-byte aligned, ld_out a multiple of 4 and >= max_len");
+  const size_t smem = ((sizeof(SelectScratch) + 15) & ~size_t(15)) + 2 * (static_cast<size_t>(max_len) + 16);
+  static size_t configured[64] = {0};   // per device
+  int dev = 0;
+  RISER_CUDA_TRY(cudaGetDevice(&dev));
+  if (smem > configured[dev & 63]) {
+    RISER_CUDA_TRY(cudaFuncSetAttribute(normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    configured[dev & 63] = smem;
+  }
+  int per_sm = 0;
+  RISER_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normalise_kernel, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = std::min(B, sm_count() * per_sm);
+  normalise_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, start, len, B, out, ld_out,
+                                                               med2_mad4);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+extern "C" int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, int B,
+                               int32_t* polya_end, int32_t* stats, int max_windows,
+                               riser_stream_t stream) {
+  RISER_REQUIRE(B >= 0, "riser_polya_end: B < 0");
+  if (B == 0) return RISER_OK;
+  RISER_REQUIRE(sig && off && n && polya_end, "riser_polya_end: null pointer");
+  RISER_REQUIRE(!stats || max_windows > 0, "riser_polya_end: stats given but max_windows <= 0");
+  const int grid = std::min(B, sm_count() * 4);
+  polya_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(sig, off, n, B, polya_end, stats, max_windows);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}

@@ -1,0 +1,171 @@
+"""Host-side mirror of riser/preprocess.py (Kit, SignalProcessor) backed by the
+sm_100a kernels in csrc/preprocess.cu.
+
+The eight methods ``control.py`` calls keep the reference's names, arguments,
+return types and error behaviour (riser/preprocess.py:29-115), so the object
+drops in behind ``SequencerControl``; the additive ``*_batch`` methods are what
+the batched loop (riser_b200/control.py) uses.  All arithmetic that produces
+signal values runs on the GPU; there is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+# riser/preprocess.py:6-12
+_MIN_INPUT_SIGNALS = 4096
+_MAX_INPUT_NT = 280
+_TRIM_RESOLUTION = 500
+_TRIM_FIXED_LENGTH_NT = 150.6
+
+
+class Kit():
+    """riser/preprocess.py:15-27."""
+    def __init__(self, sampling_hz, transloc_rate):
+        self.sampling_hz = sampling_hz
+        self.transloc_rate = transloc_rate
+
+    @classmethod
+    def create_from_version(cls, version):
+        if version == "RNA002":
+            return cls(3012, 70)
+        elif version == "RNA004":
+            return cls(4000, 130)
+        else:
+            raise Exception(f"Invalid kit version {version}")
+
+
+class RaggedBatch:
+    """int16 reads packed back to back on the device: ``sig`` [total], ``off`` int64
+    [B+1], ``n`` int32 [B].  Built from host arrays through one pinned staging
+    buffer and one H2D copy."""
+    def __init__(self, signals, device):
+        n = np.fromiter((len(s) for s in signals), dtype=np.int64, count=len(signals))
+        # keep every read 16-byte aligned so the kernels' vector loads need no peeling
+        padded = (n + 7) & ~7
+        off = np.zeros(len(signals) + 1, dtype=np.int64)
+        np.cumsum(padded, out=off[1:])
+        host = torch.empty(int(off[-1]) + 8, dtype=torch.int16).pin_memory()
+        hv = host.numpy()
+        for s, o, k in zip(signals, off[:-1], n):
+            hv[o:o + k] = s
+        self.B = len(signals)
+        self.n_host = n.astype(np.int32)
+        self.sig = host.to(device, non_blocking=True)
+        self.off = torch.from_numpy(off).to(device, non_blocking=True)
+        self.n = torch.from_numpy(self.n_host).to(device, non_blocking=True)
+        self._host = host      # keep the pinned buffer alive until the copy has run
+        self.h2d_bytes = host.numel() * 2 + off.nbytes + self.n_host.nbytes
+
+
+class SignalProcessor():
+    def __init__(self, kit):
+        self.kit = kit
+
+    # ------------------------------------------------------------ length gates
+    def get_min_length(self):
+        return _MIN_INPUT_SIGNALS
+
+    def get_max_length(self):
+        return int(_MAX_INPUT_NT / self.kit.transloc_rate * self.kit.sampling_hz)
+
+    def is_max_length(self, signal):
+        return len(signal) >= self.get_max_length()
+
+    def get_fixed_trim_length(self):
+        return int(_TRIM_FIXED_LENGTH_NT / self.kit.transloc_rate * self.kit.sampling_hz)
+
+    def should_trim_fixed_length(self, signal):
+        return len(signal) > self.get_fixed_trim_length() + self.get_max_length()
+
+    def trim_polyA_fixed_length(self, signal):
+        return signal[self.get_fixed_trim_length():]
+
+    # ------------------------------------------------------------ poly(A)
+    def get_polyA_end(self, signal):
+        """riser/preprocess.py:42-79 -> int window-start index or None."""
+        end = self.get_polyA_end_batch([signal])[0]
+        return None if end < 0 else int(end)
+
+    def trim_polyA(self, signal, read_id, cache):
+        """riser/preprocess.py:87-102 (mutates the caller's cache)."""
+        trimmed = False
+        if read_id in cache:
+            polyA_end = cache[read_id]
+        else:
+            polyA_end = self.get_polyA_end(signal)
+            if polyA_end:
+                cache[read_id] = polyA_end
+        if polyA_end:
+            signal = signal[polyA_end + 1:]
+            trimmed = True
+        return signal, trimmed
+
+    def get_polyA_end_batch(self, signals, return_stats=False):
+        """Batched get_polyA_end: list of int16 arrays -> int32 [B] (-1 = None)."""
+        device = _lib.require_device()
+        if not isinstance(signals, RaggedBatch) and len(signals) == 0:
+            return np.zeros(0, dtype=np.int32)
+        batch = signals if isinstance(signals, RaggedBatch) else RaggedBatch(
+            [np.ascontiguousarray(s, dtype=np.int16) for s in signals], device)
+        ends = self.polya_end_device(batch, return_stats=return_stats)
+        if return_stats:
+            return ends[0].cpu().numpy(), ends[1].cpu().numpy()
+        return ends.cpu().numpy()
+
+    def polya_end_device(self, batch, return_stats=False):
+        ends = torch.empty(batch.B, dtype=torch.int32, device=batch.sig.device)
+        stats, max_w = None, 0
+        if return_stats:
+            max_w = max(1, int(batch.n_host.max()) // _TRIM_RESOLUTION)
+            stats = torch.zeros(batch.B, max_w, 3, dtype=torch.int32, device=batch.sig.device)
+        _lib.check(_lib.lib().riser_polya_end(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(batch.n),
+                                              batch.B, _lib.ptr(ends), _lib.ptr(stats), max_w,
+                                              _lib.stream_ptr()), "riser_polya_end")
+        return (ends, stats) if return_stats else ends
+
+    # ------------------------------------------------------------ normalise
+    def mad_normalise(self, signal):
+        """riser/preprocess.py:108-115: float64 ndarray out (the GPU result is the
+        reference's float64 value rounded to fp32 -- the cast riser/model.py:25
+        applies anyway -- widened back to float64).  Raises ValueError on empty."""
+        signal = np.asarray(signal)
+        if signal.shape[0] == 0:
+            raise ValueError("Signal must not be empty")
+        if signal.dtype != np.int16:
+            raise TypeError("riser_b200 normalises raw int16 ADC signal (riser/client.py:47); "
+                            f"got {signal.dtype}")
+        out, _ = self.mad_normalise_batch([signal])
+        return out[0, :signal.shape[0]].double().cpu().numpy()
+
+    def mad_normalise_batch(self, signals, start=None, length=None, out=None, return_stats=False):
+        """Batched mad_normalise over ragged int16 windows.
+
+        signals: list of int16 arrays, or a RaggedBatch already on the device.
+        start / length (optional int32 arrays): window of each read
+        (``sig[start:start+length]``); default the whole read.
+        Returns (out fp32 [B, ld] on the device, lengths int32 device tensor)."""
+        device = _lib.require_device()
+        batch = signals if isinstance(signals, RaggedBatch) else RaggedBatch(
+            [np.ascontiguousarray(s, dtype=np.int16) for s in signals], device)
+        if length is None:
+            len_host = batch.n_host if start is None else batch.n_host - np.asarray(start, dtype=np.int32)
+        else:
+            len_host = np.asarray(length, dtype=np.int32)
+        max_len = int(len_host.max()) if batch.B else 0
+        if max_len > _lib.lib().riser_normalise_max_len():
+            raise ValueError(f"window of {max_len} samples exceeds riser_normalise_max_len()")
+        ld = (max_len + 3) & ~3
+        if out is None:
+            out = torch.zeros(batch.B, max(ld, 4), dtype=torch.float32, device=device)
+        start_t = None if start is None else torch.as_tensor(np.asarray(start, dtype=np.int32)).to(device)
+        len_t = batch.n if (length is None and start is None) else torch.from_numpy(len_host).to(device)
+        stats = torch.zeros(batch.B, 2, dtype=torch.int32, device=device) if return_stats else None
+        if batch.B and max_len > 0:
+            _lib.check(_lib.lib().riser_normalise(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(start_t),
+                                                  _lib.ptr(len_t), batch.B, max_len, _lib.ptr(out),
+                                                  out.stride(0), _lib.ptr(stats), _lib.stream_ptr()),
+                       "riser_normalise")
+        if return_stats:
+            return out, len_t, stats
+        return out, len_t
