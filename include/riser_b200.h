@@ -54,10 +54,12 @@ enum { RISER_MODE_ENRICH = 0, RISER_MODE_DEPLETE = 1 };
 /* Arithmetic of the convolution stack (layers 1..n-1; layer 0 and the head are
  * always fp32).  Operands are fp16 (10-bit mantissa, the same as tf32, at twice
  * the tensor rate); accumulation is fp32 in TMEM.
- *   F16    : one tcgen05 pass, weights rounded to fp16.
- *   F16_W2 : two passes, weights split hi + lo fp16 (weights exact to ~22 bits);
- *            only the activation rounding remains.                              */
-enum { RISER_PREC_F16 = 0, RISER_PREC_F16_W2 = 1 };
+ *   F16    : one tcgen05 pass; weights and activations rounded to fp16.
+ *   F16_W2 : two passes; weights split hi + lo fp16 (exact to ~22 bits), only the
+ *            activation rounding remains.
+ *   F16_X3 : three passes; weights AND activations split hi + lo
+ *            (W_hi a_hi + W_lo a_hi + W_hi a_lo): fp32-class results.           */
+enum { RISER_PREC_F16 = 0, RISER_PREC_F16_W2 = 1, RISER_PREC_F16_X3 = 2 };
 
 int riser_version(void);
 const char* riser_last_error(void);
@@ -139,6 +141,14 @@ int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32
 
 /* Number of kernels one riser_forward launches (for gpu_launches accounting). */
 int riser_forward_launches(const riser_plan* p);
+
+/* Introspection for tests / profiling: layer i (1..n_layers) reads (i < n) or, for
+ * i == n_layers, the head reads, an activation buffer at workspace + *offset laid out
+ * [B * *rows_per_read][*channels_padded], fp16 for i < n_layers, fp32 for i == n_layers.
+ * *channels = unpadded channel count, *n_tile = the tcgen05 N tile of the layer that
+ * WROTE it.                                                                      */
+int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
+                          int* channels_padded, int* channels, int* n_tile);
 
 /* Replaces the decision rule of riser/control.py:75-82 for M models:
  * probs [M, B, 2]; len [B] = post-trim window length, 0 = read was skipped

@@ -2,5 +2,6 @@
 path (trim -> normalise -> 1-D CNN -> decision) behind the reference's
 Kit / SignalProcessor / Model / SequencerControl call surface."""
 from .preprocess import Kit, SignalProcessor, RaggedBatch      # noqa: F401
+from .model import Model, decide, PREC_F16, PREC_F16_W2, PREC_F16_X3   # noqa: F401
 
-__all__ = ["Kit", "SignalProcessor", "RaggedBatch"]
+__all__ = ["Kit", "SignalProcessor", "RaggedBatch", "Model", "decide", "PREC_F16", "PREC_F16_W2", "PREC_F16_X3"]

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,8 @@ constexpr int kMaxNTile = 256;        // UMMA N limit
 constexpr int kTmemCols = 512;        // two accumulator buffers of up to 256 columns
 constexpr int kConvThreads = 192;     // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue
 constexpr int kMinLen = 4096;         // riser/preprocess.py:8
+constexpr int kDefaultConvImpl = 1;   // see riser_plan_create
+constexpr int kMaxStages = 12;        // operand ring depth (deep: early layers are latency bound)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -58,6 +61,8 @@ struct LayerPack {
   __half* w = nullptr;    // [passes][3][cout_p][cin_p] fp16 (layers >= 1)
   float* w0 = nullptr;    // layer 0 only: fp32 [cout][3]
   float* bias = nullptr;  // fp32 [cout_p], zero padded
+  float w_inv_scale = 1.f;  // weights are stored multiplied by a power of two (keeps the fp16 lo
+                            // plane out of the subnormal range); the epilogue undoes it exactly
 };
 
 }  // namespace
@@ -66,7 +71,8 @@ struct LayerPack {
 struct riser_model {
   int n_layers = 0;
   int precision = 0;
-  int passes = 1;
+  int passes = 1;       // weight planes
+  int act_planes = 1;   // activation planes
   int device = 0;
   int sm_count = 148;
   riser::LayerPack layer[riser::kMaxLayers];
@@ -85,6 +91,15 @@ struct ConvArgs {
   int rows_in, Lp_in, Lp_out, shift;
   int cin_p, cout_p, n_tile, n_tiles, m_tiles, k_blocks, passes, stages, out_fp32;
   uint32_t idesc;
+  // v2 kernel (single A load per K block, shifted descriptors per tap)
+  int n_asteps;          // A loads per K block: 1, or 2 when the activation lo plane is used
+  int a_plane[2];        // activation plane (0 = hi, 1 = lo) of each A step
+  int n_w[2];            // weight planes multiplied against each A step
+  int w_plane[2][2];
+  int n_wplanes;         // weight planes resident / in the tensor
+  int out_planes;        // 1, or 2 = write hi and lo fp16 planes
+  int a_stages, b_stages, resident, base_off_mode;
+  float w_inv_scale;
 };
 
 struct LayerPlan {
@@ -99,7 +114,7 @@ struct LayerPlan {
 
 struct riser_plan {
   const riser_model* model = nullptr;
-  int B = 0, max_len = 0;
+  int B = 0, max_len = 0, impl = 0;
   int Lmax[riser::kMaxLayers + 1];
   int Lp[riser::kMaxLayers + 1];
   size_t act_off[riser::kMaxLayers + 1];
@@ -111,25 +126,29 @@ namespace riser {
 namespace {
 
 // ------------------------------------------------------------------------------------
-// layer 0: x fp32 [B, ld_x] -> act_1 [B*Lp1][cout_p] fp16.  One thread per output row.
+// layer 0: x fp32 [B, ld_x] -> act_1 [B*Lp1][cout_p] fp16.  One thread per (output row,
+// 8-channel group): consecutive lanes write consecutive 16-byte chunks (coalesced).
 __global__ void __launch_bounds__(256)
 layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ len0,
               const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ out,
-              int B, int Lp1, int cout, int cout_p) {
+              int B, int Lp1, int cout, int cout_p, int planes) {
   __shared__ float sw[64 * 3];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < cout_p * 3; i += blockDim.x) sw[i] = (i < cout * 3) ? w[i] : 0.f;
   for (int i = threadIdx.x; i < cout_p; i += blockDim.x) sb[i] = (i < cout) ? bias[i] : 0.f;
   __syncthreads();
-  const int64_t total = static_cast<int64_t>(B) * Lp1;
-  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < total;
-       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(r / Lp1);
-    const int tp = static_cast<int>(r - static_cast<int64_t>(b) * Lp1);
+  const uint32_t groups = cout_p >> 3;
+  const uint32_t total = static_cast<uint32_t>(B) * Lp1 * groups;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t r = idx / groups;
+    const int c8 = static_cast<int>(idx - r * groups);
+    const int b = static_cast<int>(r / static_cast<uint32_t>(Lp1));
+    const int tp = static_cast<int>(r - static_cast<uint32_t>(b) * Lp1);
     const int L = len0[b];
-    uint4* o = reinterpret_cast<uint4*>(out + r * cout_p);
+    uint4* o = reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * cout_p * planes) + c8;
     if (tp >= (L >> 1)) {
-      for (int c8 = 0; c8 < cout_p / 8; ++c8) o[c8] = make_uint4(0, 0, 0, 0);
+      *o = make_uint4(0, 0, 0, 0);
+      if (planes == 2) o[groups] = make_uint4(0, 0, 0, 0);
       continue;
     }
     const float* xr = x + static_cast<int64_t>(b) * ld_x;
@@ -137,31 +156,32 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
     const float xm1 = (t > 0) ? xr[t - 1] : 0.f;
     const float2 x01 = *reinterpret_cast<const float2*>(xr + t);
     const float x2 = (t + 2 < L) ? xr[t + 2] : 0.f;
-    for (int c8 = 0; c8 < cout_p / 8; ++c8) {
-      __half2 h[4];
+    __half2 h[4], hl[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v[2];
+    for (int j = 0; j < 4; ++j) {
+      float v[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = c8 * 8 + 2 * j + e;
-          const float w0 = sw[c * 3], w1 = sw[c * 3 + 1], w2 = sw[c * 3 + 2], bb = sb[c];
-          const float y0 = fmaf(w2, x01.y, fmaf(w1, x01.x, fmaf(w0, xm1, bb)));
-          const float y1 = fmaf(w2, x2, fmaf(w1, x01.y, fmaf(w0, x01.x, bb)));
-          v[e] = fmaxf(fmaxf(y0, y1), 0.f);
-        }
-        h[j] = __floats2half2_rn(v[0], v[1]);
+      for (int e = 0; e < 2; ++e) {
+        const int c = c8 * 8 + 2 * j + e;
+        const float w0 = sw[c * 3], w1 = sw[c * 3 + 1], w2 = sw[c * 3 + 2], bb = sb[c];
+        const float y0 = fmaf(w2, x01.y, fmaf(w1, x01.x, fmaf(w0, xm1, bb)));
+        const float y1 = fmaf(w2, x2, fmaf(w1, x01.y, fmaf(w0, x01.x, bb)));
+        v[e] = fminf(fmaxf(fmaxf(y0, y1), 0.f), 65504.f);
       }
-      o[c8] = *reinterpret_cast<uint4*>(h);
+      h[j] = __floats2half2_rn(v[0], v[1]);
+      const float2 back = __half22float2(h[j]);
+      hl[j] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
     }
+    *o = *reinterpret_cast<uint4*>(h);
+    if (planes == 2) o[groups] = *reinterpret_cast<uint4*>(hl);
   }
 }
 
 // ------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution with fused bias + ReLU + MaxPool(2,2) + length mask.
 struct ConvSmem {
-  uint64_t full[8];
-  uint64_t empty[8];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -179,7 +199,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 template <int W>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* bias_s, int col0,
                                                bool odd, bool valid, bool writable, void* out_row,
-                                               bool out_fp32) {
+                                               bool out_fp32, int lo_plane_off = 0, float inv_scale = 1.f) {
   constexpr int H = W / 2;
   float r[H];
 #pragma unroll
@@ -187,7 +207,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const flo
     const float mine = __uint_as_float(odd ? v[j + H] : v[j]);
     const float send = __uint_as_float(odd ? v[j] : v[j + H]);
     const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    const float bsum = fmaxf(mine, recv) + bias_s[col0 + (odd ? H : 0) + j];
+    const float bsum = fmaf(fmaxf(mine, recv), inv_scale, bias_s[col0 + (odd ? H : 0) + j]);
     r[j] = valid ? fmaxf(bsum, 0.f) : 0.f;
   }
   if (!writable) return;
@@ -202,6 +222,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const flo
     for (int j = 0; j < H / 8; ++j)
       o[j] = make_uint4(pack_half2(r[8 * j], r[8 * j + 1]), pack_half2(r[8 * j + 2], r[8 * j + 3]),
                         pack_half2(r[8 * j + 4], r[8 * j + 5]), pack_half2(r[8 * j + 6], r[8 * j + 7]));
+    if (lo_plane_off) {   // residual plane: a = hi + lo with hi = fp16(a), lo = fp16(a - hi)
+#pragma unroll
+      for (int j = 0; j < H; ++j) r[j] -= __half2float(__float2half_rn(fminf(r[j], 65504.f)));
+      uint4* ol = reinterpret_cast<uint4*>(static_cast<__half*>(out_row) + lo_plane_off + c);
+#pragma unroll
+      for (int j = 0; j < H / 8; ++j)
+        ol[j] = make_uint4(pack_half2(r[8 * j], r[8 * j + 1]), pack_half2(r[8 * j + 2], r[8 * j + 3]),
+                           pack_half2(r[8 * j + 4], r[8 * j + 5]), pack_half2(r[8 * j + 6], r[8 * j + 7]));
+    }
   }
 }
 
@@ -339,13 +368,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint32_t v[32];
         tmem_ld_32x32(t_addr + col, v);
         tmem_ld_wait();
-        epilogue_chunk<32>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32);
+        epilogue_chunk<32>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, 0, a.w_inv_scale);
       }
       if (col < a.n_tile) {
         uint32_t v[16];
         tmem_ld_32x16(t_addr + col, v);
         tmem_ld_wait();
-        epilogue_chunk<16>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32);
+        epilogue_chunk<16>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, 0, a.w_inv_scale);
       }
       tc_fence_before();
       __syncwarp();
@@ -362,18 +391,247 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------
-// head: masked global average pool -> Linear(C, 2) -> softmax.  One warp per read.
-__global__ void __launch_bounds__(256)
+// v2: one A load per K block (130 rows: the 128-row tile plus one halo row on each side);
+// the three taps read it through descriptors whose start address is shifted by 0/1/2 rows.
+// Weights are either resident in shared memory for the whole kernel (layers whose three
+// taps fit: one N tile) or streamed through their own ring.
+constexpr int kARows = kBlockM + 2;
+constexpr int kAStageBytes = 136 * 128;     // ring stride, multiple of 1024
+constexpr int kATxBytes = kARows * 128;
+constexpr int kMaxAStages = 8, kMaxBStages = 8;
+
+struct ConvSmem2 {
+  uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  uint64_t w_full;
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  float bias[2][kMaxNTile];
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t smem_addr, uint32_t base_offset) {
+  return umma_desc_sw128(smem_addr) | (static_cast<uint64_t>(base_offset & 7) << 49);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const ConvArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t b_bytes = a.n_tile * kBlockK * 2;
+  unsigned char* a_ring = base;
+  unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAStageBytes;
+  const size_t b_region_bytes = a.resident ? static_cast<size_t>(a.n_wplanes) * 3 * a.k_blocks * b_bytes
+                                           : static_cast<size_t>(a.b_stages) * b_bytes;
+  ConvSmem2& s = *reinterpret_cast<ConvSmem2*>(b_region + b_region_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_total = a.m_tiles * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int i = 0; i < a.a_stages; ++i) {
+      mbar_init(&s.a_full[i], 1);
+      mbar_init(&s.a_empty[i], 1);
+    }
+    for (int i = 0; i < a.b_stages; ++i) {
+      mbar_init(&s.b_full[i], 1);
+      mbar_init(&s.b_empty[i], 1);
+    }
+    mbar_init(&s.w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      mbar_init(&s.tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s.tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (a.resident) {
+        mbar_arrive_expect_tx(&s.w_full, static_cast<uint32_t>(b_region_bytes));
+        for (int wp = 0; wp < a.n_wplanes; ++wp)
+          for (int tap = 0; tap < 3; ++tap)
+            for (int kb = 0; kb < a.k_blocks; ++kb)
+              tma_load_2d(b_region + static_cast<size_t>((wp * 3 + tap) * a.k_blocks + kb) * b_bytes, &tm_b,
+                          &s.w_full, kb * kBlockK, (wp * 3 + tap) * a.cout_p);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int m0 = (tile / a.n_tiles) * kBlockM;
+        const int n0 = (tile % a.n_tiles) * a.n_tile;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          for (int as = 0; as < a.n_asteps; ++as) {
+            mbar_wait(&s.a_empty[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&s.a_full[sa], kATxBytes);
+            tma_load_2d(a_ring + static_cast<size_t>(sa) * kAStageBytes, &tm_a, &s.a_full[sa],
+                        a.a_plane[as] * a.cin_p + kb * kBlockK, m0 - 1);
+            if (++sa == a.a_stages) {
+              sa = 0;
+              pa ^= 1;
+            }
+            if (!a.resident) {
+              for (int wi = 0; wi < a.n_w[as]; ++wi)
+                for (int tap = 0; tap < 3; ++tap) {
+                  mbar_wait(&s.b_empty[sb], pb ^ 1);
+                  mbar_arrive_expect_tx(&s.b_full[sb], b_bytes);
+                  tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb],
+                              kb * kBlockK, (a.w_plane[as][wi] * 3 + tap) * a.cout_p + n0);
+                  if (++sb == a.b_stages) {
+                    sb = 0;
+                    pb ^= 1;
+                  }
+                }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      if (a.resident) {
+        mbar_wait(&s.w_full, 0);
+        tc_fence_after();
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMaxNTile;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          const int nk = min(kBlockK / 16, (a.cin_p - kb * kBlockK) / 16);
+          for (int as = 0; as < a.n_asteps; ++as) {
+            mbar_wait(&s.a_full[sa], pa);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_ring + static_cast<size_t>(sa) * kAStageBytes);
+            for (int wi = 0; wi < a.n_w[as]; ++wi) {
+              for (int tap = 0; tap < 3; ++tap) {
+                uint32_t b_addr;
+                if (a.resident) {
+                  b_addr = smem_u32(b_region +
+                                    static_cast<size_t>((a.w_plane[as][wi] * 3 + tap) * a.k_blocks + kb) * b_bytes);
+                } else {
+                  mbar_wait(&s.b_full[sb], pb);
+                  tc_fence_after();
+                  b_addr = smem_u32(b_region + static_cast<size_t>(sb) * b_bytes);
+                }
+                const uint64_t da = umma_desc_sw128_off(a_addr + tap * 128, a.base_off_mode ? tap : 0);
+                const uint64_t db = umma_desc_sw128(b_addr);
+                for (int k = 0; k < nk; ++k) {
+                  umma_f16(d_tmem, da + 2 * k, db + 2 * k, a.idesc, accumulate);
+                  accumulate = 1;
+                }
+                if (!a.resident) {
+                  umma_commit(&s.b_empty[sb]);
+                  if (++sb == a.b_stages) {
+                    sb = 0;
+                    pb ^= 1;
+                  }
+                }
+              }
+            }
+            umma_commit(&s.a_empty[sa]);
+            if (++sa == a.a_stages) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+        umma_commit(&s.tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    const bool odd = lane & 1;
+    const int row_elems = a.cout_p * a.out_planes;
+    const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / a.n_tiles) * kBlockM;
+      const int n0 = (tile % a.n_tiles) * a.n_tile;
+      for (int i = et; i < a.n_tile; i += 128) s.bias[acc][i] = a.bias[n0 + i];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      const int r_even = (m0 + 32 * q + lane) & ~1;
+      bool valid = false, writable = false;
+      int64_t out_row = 0;
+      if (r_even < a.rows_in) {
+        const int b = r_even / a.Lp_in;
+        const int tp = (r_even - b * a.Lp_in) >> 1;
+        valid = tp < (a.len0[b] >> a.shift);
+        writable = tp < a.Lp_out;
+        out_row = static_cast<int64_t>(b) * a.Lp_out + tp;
+      }
+      void* orow = a.out_fp32
+                       ? static_cast<void*>(static_cast<float*>(a.out) + out_row * row_elems + n0)
+                       : static_cast<void*>(static_cast<__half*>(a.out) + out_row * row_elems + n0);
+
+      mbar_wait(&s.tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * kMaxNTile;
+      int col = 0;
+      for (; col + 32 <= a.n_tile; col += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + col, v);
+        tmem_ld_wait();
+        epilogue_chunk<32>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, lo_off, a.w_inv_scale);
+      }
+      if (col < a.n_tile) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_addr + col, v);
+        tmem_ld_wait();
+        epilogue_chunk<16>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, lo_off, a.w_inv_scale);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// head: masked global average pool -> Linear(C, 2) -> softmax.  One CTA per read.
+constexpr int kHeadThreads = 128;
+__global__ void __launch_bounds__(kHeadThreads)
 head_kernel(const float* __restrict__ act, const int32_t* __restrict__ len0, const float* __restrict__ fc_w,
             const float* __restrict__ fc_b, float* __restrict__ probs, float* __restrict__ feat, int B,
             int Lp, int cp, int c, int shift) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B) return;
-  const int b = warp;
+  __shared__ float red[2][kHeadThreads / 32];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = len0[b] >> shift;
   if (L <= 0) {   // shorter than 4096 samples: the reference raises in max_pool1d
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       probs[2 * b] = nanf("");
       probs[2 * b + 1] = nanf("");
     }
@@ -382,13 +640,13 @@ head_kernel(const float* __restrict__ act, const int32_t* __restrict__ len0, con
   const float* rows = act + static_cast<int64_t>(b) * Lp * cp;
   const float inv = 1.f / static_cast<float>(L);
   float l0 = 0.f, l1 = 0.f;
-  for (int ch = lane; ch < c; ch += 32) {
+  for (int ch = threadIdx.x; ch < c; ch += kHeadThreads) {
     float sum = 0.f;
     for (int t = 0; t < L; ++t) sum += rows[static_cast<int64_t>(t) * cp + ch];
     const float f = sum * inv;
     if (feat) feat[static_cast<int64_t>(b) * c + ch] = f;
-    l0 = fmaf(f, fc_w[ch], l0);
-    l1 = fmaf(f, fc_w[c + ch], l1);
+    l0 = fmaf(f, __ldg(fc_w + ch), l0);
+    l1 = fmaf(f, __ldg(fc_w + c + ch), l1);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -396,8 +654,17 @@ head_kernel(const float* __restrict__ act, const int32_t* __restrict__ len0, con
     l1 += __shfl_xor_sync(0xffffffffu, l1, d);
   }
   if (lane == 0) {
-    l0 += fc_b[0];
-    l1 += fc_b[1];
+    red[0][warp] = l0;
+    red[1][warp] = l1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    l0 = fc_b[0];
+    l1 = fc_b[1];
+    for (int w = 0; w < kHeadThreads / 32; ++w) {
+      l0 += red[0][w];
+      l1 += red[1][w];
+    }
     const float m = fmaxf(l0, l1);
     const float e0 = expf(l0 - m), e1 = expf(l1 - m);
     const float inv_s = 1.f / (e0 + e1);
@@ -485,10 +752,17 @@ size_t plan_offsets(const riser_model* m, int B, const int* Lp, size_t* off) {
   size_t cur = 0;
   for (int i = 1; i <= m->n_layers; ++i) {
     off[i] = cur;
-    const size_t elt = (i == m->n_layers) ? 4 : 2;
-    cur += align_up(static_cast<size_t>(B) * Lp[i] * m->layer[i - 1].cout_p * elt, 1024);
+    const bool last = (i == m->n_layers);
+    const size_t elt = last ? 4 : 2;
+    const size_t planes = last ? 1 : m->act_planes;
+    cur += align_up(static_cast<size_t>(B) * Lp[i] * m->layer[i - 1].cout_p * planes * elt, 1024);
   }
   return cur;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 }  // namespace
@@ -502,7 +776,7 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   RISER_REQUIRE(out && channels && conv_w && conv_b && fc_w && fc_b, "riser_model_create: null pointer");
   RISER_REQUIRE(n_layers >= 2 && n_layers <= kMaxLayers, "riser_model_create: n_layers %d outside [2, %d]",
                 n_layers, kMaxLayers);
-  RISER_REQUIRE(precision == RISER_PREC_F16 || precision == RISER_PREC_F16_W2,
+  RISER_REQUIRE(precision >= RISER_PREC_F16 && precision <= RISER_PREC_F16_X3,
                 "riser_model_create: unknown precision %d", precision);
   RISER_REQUIRE(channels[0] <= 64, "riser_model_create: layer 0 supports at most 64 output channels");
   RISER_CUDA_TRY(cudaSetDevice(device));
@@ -513,7 +787,8 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   riser_model* m = new riser_model();
   m->n_layers = n_layers;
   m->precision = precision;
-  m->passes = (precision == RISER_PREC_F16_W2) ? 2 : 1;
+  m->passes = (precision == RISER_PREC_F16) ? 1 : 2;           // weight planes (hi [, lo])
+  m->act_planes = (precision == RISER_PREC_F16_X3) ? 2 : 1;    // activation planes (hi [, lo])
   m->device = device;
   cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
   int cin = 1, cin_p = 1;
@@ -533,14 +808,24 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
       RISER_CUDA_TRY(cudaMalloc(&L.w0, sizeof(float) * L.cout * 3));
       RISER_CUDA_TRY(cudaMemcpy(L.w0, conv_w[0], sizeof(float) * L.cout * 3, cudaMemcpyHostToDevice));
     } else {
-      // [pass][tap][cout_p][cin_p]: tap-major so that one 2-D tensor map serves all taps
+      // [plane][tap][cout_p][cin_p]: tap-major so that one 2-D tensor map serves all taps
       const size_t per_pass = static_cast<size_t>(3) * L.cout_p * L.cin_p;
       std::vector<__half> w(per_pass * m->passes, __float2half(0.f));
       const float* src = conv_w[i];   // [cout][cin][3]
+      float wmax = 0.f;
+      for (size_t k = 0; k < static_cast<size_t>(L.cout) * L.cin * 3; ++k) wmax = std::max(wmax, std::fabs(src[k]));
+      int e = 0;
+      if (wmax > 0.f && std::isfinite(wmax)) {
+        std::frexp(wmax, &e);          // wmax = f * 2^e, f in [0.5, 1)
+        e = 12 - e;                    // scaled max magnitude in [2^11, 2^12)
+        e = std::max(-24, std::min(24, e));
+      }
+      const float scale = std::ldexp(1.f, e);
+      L.w_inv_scale = std::ldexp(1.f, -e);
       for (int co = 0; co < L.cout; ++co)
         for (int ci = 0; ci < L.cin; ++ci)
           for (int tap = 0; tap < 3; ++tap) {
-            const float v = src[(static_cast<size_t>(co) * L.cin + ci) * 3 + tap];
+            const float v = src[(static_cast<size_t>(co) * L.cin + ci) * 3 + tap] * scale;
             const __half hi = __float2half_rn(v);
             const size_t idx = (static_cast<size_t>(tap) * L.cout_p + co) * L.cin_p + ci;
             w[idx] = hi;
@@ -592,13 +877,18 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
   p->B = B;
   p->max_len = max_len;
   p->ws = static_cast<char*>(workspace);
+  // RISER_CONV_IMPL: 0 = v1 (one A load per tap), 1 = v2 shifted descriptors (base_offset 0),
+  // 2 = v2 with base_offset = tap.  Development switch; the default is the validated one.
+  p->impl = env_int("RISER_CONV_IMPL", kDefaultConvImpl);
+  const bool allow_resident = env_int("RISER_CONV_RESIDENT", 1) != 0;
   plan_lengths(m, max_len, p->Lmax, p->Lp);
   const size_t need = plan_offsets(m, B, p->Lp, p->act_off);
   if (workspace_bytes < need) {
     delete p;
     return fail(RISER_ENOMEM, "riser_plan_create: workspace %zu < %zu bytes", workspace_bytes, need);
   }
-  RISER_REQUIRE(static_cast<int64_t>(B) * p->Lp[1] < (int64_t(1) << 31), "riser_plan_create: B * L too large");
+  RISER_REQUIRE(static_cast<int64_t>(B) * p->Lp[1] * 8 < (int64_t(1) << 31), "riser_plan_create: B * L too large");
+  RISER_REQUIRE(p->impl != 0 || m->act_planes == 1, "riser_plan_create: the v1 kernel has no X3 mode");
   RISER_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, as_stream(stream)));
   int max_smem = 0;
   RISER_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
@@ -606,13 +896,16 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const LayerPack& L = m->layer[i];
     LayerPlan& lp = p->layer[i];
     const int rows_in = B * p->Lp[i];
-    int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], L.cin_p, rows_in, kBlockM);
+    const bool last = (i == m->n_layers - 1);
+    int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
+                       p->impl == 0 ? kBlockM : kARows);
     if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile);
     if (st) {
       delete p;
       return st;
     }
     ConvArgs& a = lp.args;
+    std::memset(&a, 0, sizeof(a));
     a.bias = L.bias;
     a.len0 = nullptr;
     a.out = p->ws + p->act_off[i + 1];
@@ -627,18 +920,54 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.m_tiles = (rows_in + kBlockM - 1) / kBlockM;
     a.k_blocks = (L.cin_p + kBlockK - 1) / kBlockK;
     a.passes = m->passes;
-    a.out_fp32 = (i == m->n_layers - 1) ? 1 : 0;
+    a.out_fp32 = last ? 1 : 0;
+    a.out_planes = last ? 1 : m->act_planes;
     a.idesc = umma_idesc_f16(kBlockM, L.n_tile);
-    const size_t stage_bytes = static_cast<size_t>(kBlockM) * kBlockK * 2 + static_cast<size_t>(L.n_tile) * kBlockK * 2;
-    const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
-    int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage_bytes);
-    stages = std::max(2, std::min(8, stages));
-    stages = std::min(stages, std::max(2, a.passes * 3 * a.k_blocks));
-    a.stages = stages;
-    lp.smem = fixed + stages * stage_bytes;
+    a.w_inv_scale = L.w_inv_scale;
+    const size_t b_bytes = static_cast<size_t>(L.n_tile) * kBlockK * 2;
+    if (p->impl == 0) {
+      const size_t stage_bytes = static_cast<size_t>(kBlockM) * kBlockK * 2 + b_bytes;
+      const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
+      int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage_bytes);
+      a.stages = std::max(2, std::min(kMaxStages, stages));
+      lp.smem = fixed + a.stages * stage_bytes;
+    } else {
+      a.base_off_mode = (p->impl == 2) ? 1 : 0;
+      a.n_wplanes = m->passes;
+      // A steps: hi plane x {W_hi [, W_lo]}, then (X3) lo plane x {W_hi}
+      a.n_asteps = m->act_planes;
+      a.a_plane[0] = 0;
+      a.n_w[0] = m->passes;
+      a.w_plane[0][0] = 0;
+      a.w_plane[0][1] = 1;
+      a.a_plane[1] = 1;
+      a.n_w[1] = 1;
+      a.w_plane[1][0] = 0;
+      const size_t fixed = 1024 + sizeof(ConvSmem2) + 64;
+      const size_t avail = static_cast<size_t>(max_smem) - fixed;
+      const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
+      const int min_a = 3;
+      if (allow_resident && L.n_tiles == 1 && w_all + static_cast<size_t>(min_a) * kAStageBytes <= avail) {
+        a.resident = 1;
+        a.b_stages = 1;
+        a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / kAStageBytes));
+        lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * kAStageBytes;
+      } else {
+        a.resident = 0;
+        // split the budget: A ring gets ~1/3 (at least 2 stages), B ring the rest
+        int a_st = std::max(2, std::min<int>(4, static_cast<int>(avail / 3 / kAStageBytes)));
+        int b_st = static_cast<int>((avail - static_cast<size_t>(a_st) * kAStageBytes) / b_bytes);
+        b_st = std::max(2, std::min(kMaxBStages, b_st));
+        a_st = std::min<int>(kMaxAStages, static_cast<int>((avail - static_cast<size_t>(b_st) * b_bytes) / kAStageBytes));
+        a.a_stages = a_st;
+        a.b_stages = b_st;
+        lp.smem = fixed + static_cast<size_t>(a_st) * kAStageBytes + static_cast<size_t>(b_st) * b_bytes;
+      }
+    }
     lp.grid = std::min(a.m_tiles * a.n_tiles, m->sm_count);
   }
   RISER_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  RISER_CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   *out = p;
   return RISER_OK;
 }
@@ -650,6 +979,19 @@ extern "C" int riser_plan_destroy(riser_plan* p) {
 
 extern "C" int riser_forward_launches(const riser_plan* p) { return p ? p->model->n_layers + 1 : 0; }
 
+extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
+                                     int* channels_padded, int* channels, int* n_tile) {
+  RISER_REQUIRE(p && offset && rows_per_read && channels_padded && channels && n_tile,
+                "riser_plan_layer_info: null pointer");
+  RISER_REQUIRE(i >= 1 && i <= p->model->n_layers, "riser_plan_layer_info: layer %d out of range", i);
+  *offset = static_cast<int64_t>(p->act_off[i]);
+  *rows_per_read = p->Lp[i];
+  *channels_padded = p->model->layer[i - 1].cout_p * (i == p->model->n_layers ? 1 : p->model->act_planes);
+  *channels = p->model->layer[i - 1].cout;
+  *n_tile = p->model->layer[i - 1].n_tile;
+  return RISER_OK;
+}
+
 extern "C" int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len, float* probs,
                              float* feat, riser_stream_t stream) {
   RISER_REQUIRE(p && x && len && probs, "riser_forward: null pointer");
@@ -659,24 +1001,26 @@ extern "C" int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, 
   cudaStream_t st = as_stream(stream);
   {
     const LayerPack& L = m->layer[0];
-    const int64_t total = static_cast<int64_t>(p->B) * p->Lp[1];
-    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 16));
+    const int64_t total = static_cast<int64_t>(p->B) * p->Lp[1] * (L.cout_p / 8);
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 32));
     layer0_kernel<<<grid, 256, 0, st>>>(x, ld_x, len, L.w0, L.bias,
                                         reinterpret_cast<__half*>(p->ws + p->act_off[1]), p->B, p->Lp[1],
-                                        L.cout, L.cout_p);
+                                        L.cout, L.cout_p, m->act_planes);
     RISER_CUDA_TRY(cudaGetLastError());
   }
   for (int i = 1; i < m->n_layers; ++i) {
     const LayerPlan& lp = p->layer[i];
     ConvArgs a = lp.args;
     a.len0 = len;
-    conv_tc_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+    if (p->impl == 0)
+      conv_tc_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+    else
+      conv_tc2_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
     RISER_CUDA_TRY(cudaGetLastError());
   }
   {
     const int n = m->n_layers;
-    const int grid = (p->B * 32 + 255) / 256;
-    head_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(p->ws + p->act_off[n]), len, m->fc_w,
+    head_kernel<<<p->B, kHeadThreads, 0, st>>>(reinterpret_cast<const float*>(p->ws + p->act_off[n]), len, m->fc_w,
                                       m->fc_b, probs, feat, p->B, p->Lp[n], m->layer[n - 1].cout_p, m->c_last, n);
     RISER_CUDA_TRY(cudaGetLastError());
   }

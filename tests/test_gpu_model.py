@@ -1,0 +1,163 @@
+"""GPU parity of the network forward (csrc/convnet.cu through the C ABI) against the
+oracle (torch CPU fp32 restatement of riser/nets/cnn.py + riser/model.py) and the
+golden probabilities produced by the reference's own Model.classify.
+
+Tolerances (north star): softmax probabilities within 1e-3 absolute; decisions identical
+except where the reference probability lies within 1e-3 of the threshold."""
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import preprocess_oracle as pp
+from oracle import convnet_oracle as net
+from oracle import control_oracle as ctl
+from oracle.refshim import AttrDict
+from riser_b200 import Model, decide, synth, PREC_F16, PREC_F16_W2, PREC_F16_X3
+from tests.golden import make_golden_params as P
+
+pytestmark = pytest.mark.gpu
+LOG = logging.getLogger("test")
+CFG = AttrDict({"cnn": {"n_layers": 12, "depth": 1, "channels": synth.CHANNELS, "kernels": [3] * 12,
+                        "n_classes": 2, "classifier": "gap_fc"}})
+# north-star bar: 1e-3 absolute.  X3 (the default) meets it with margin (observed max 1.5e-4,
+# limited by the tensor cores' truncating fp32 accumulation); W2 / F16 are opt-in fast modes.
+PROB_TOL = {PREC_F16_X3: 1e-3, PREC_F16_W2: 2e-3, PREC_F16: 5e-3}   # F16 = opt-in fast mode, outside the 1e-3 bar
+
+
+def to_device_batch(normed, ld=None):
+    n = np.array([len(x) for x in normed], dtype=np.int32)
+    ld = ld or int((n.max() + 3) & ~3)
+    x = torch.zeros(len(normed), ld, dtype=torch.float32)
+    for b, v in enumerate(normed):
+        x[b, :len(v)] = torch.from_numpy(np.asarray(v, dtype=np.float64)).float()
+    return x.cuda(), torch.from_numpy(n).cuda()
+
+
+def oracle_layers(state, x):
+    """Per-layer pooled activations [C, L_i] of one read (fp32)."""
+    h = x.view(1, 1, -1)
+    outs = []
+    for i in range(12):
+        h = F.max_pool1d(F.relu(F.conv1d(h, state[f"layers.{i}.0.weight"], state[f"layers.{i}.0.bias"],
+                                         padding="same")), 2, 2)
+        outs.append(h[0])
+    return outs
+
+
+@pytest.mark.parametrize("impl,precision", [(0, PREC_F16), (0, PREC_F16_W2), (1, PREC_F16), (1, PREC_F16_W2),
+                                            (1, PREC_F16_X3)])
+def test_every_layer_against_oracle(impl, precision, monkeypatch):
+    monkeypatch.setenv("RISER_CONV_IMPL", str(impl))
+    rng = np.random.default_rng(0)
+    lengths = [4096, 5001, 7108, 12048, 12047, 8615, 4097]
+    normed = [pp.mad_normalise(synth.body(rng, n)) for n in lengths]
+    state = synth.state_dict(0)
+    model = Model(state, CFG, LOG, "mRNA", precision=precision)
+    x, lens = to_device_batch(normed)
+    feat = torch.zeros(len(lengths), 1702, device="cuda")
+    probs = model.classify_batch(x, lens, max_len=12048, feat=feat)
+    torch.cuda.synchronize()
+    plan = model.plan(len(lengths), 12048)
+    report = []
+    for b, v in enumerate(normed):
+        want = oracle_layers(state, torch.from_numpy(np.asarray(v, dtype=np.float64)).float())
+        for i in range(1, 13):
+            act = plan.activation(i, 12, planes=2 if precision == PREC_F16_X3 else 1)[b].float().cpu()
+            w = want[i - 1].T                                  # [L_i, C]
+            L = w.shape[0]
+            err = (act[:L] - w).abs().max().item()
+            scale = w.abs().max().item()
+            tail = act[L:].abs().max().item() if act.shape[0] > L else 0.0
+            report.append((b, i, L, err / scale, tail))
+    tol = 5e-4 if precision == PREC_F16_X3 else 1e-2
+    bad = [r for r in report if r[3] > tol or r[4] != 0.0]
+    assert not bad, "layer mismatches (read, layer, L, rel err, tail max): %s" % bad[:12]
+    want_feat = net.features(state, torch.zeros(0)) if False else None
+    ofeat = torch.stack([net.features(state, torch.from_numpy(np.asarray(v, dtype=np.float64)).float()[None])[0]
+                         for v in normed])
+    rel = ((feat.cpu() - ofeat).norm() / ofeat.norm()).item()
+    assert rel < (1e-4 if precision == PREC_F16_X3 else 2e-3), rel
+    want_p = net.classify_ragged(state, normed)
+    assert np.abs(probs.cpu().numpy() - want_p).max() < PROB_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", [PREC_F16, PREC_F16_W2, PREC_F16_X3])
+def test_probs_against_reference_golden(golden_dir, precision):
+    g = np.load(os.path.join(golden_dir, "convnet_probs.npz"))
+    bodies = P.norm_inputs()
+    normed = [pp.mad_normalise(x) for x in bodies]
+    x, lens = to_device_batch(normed)
+    worst = {}
+    for target in g["targets"]:
+        model = Model(synth.state_dict(synth.TARGET_SEEDS[str(target)]), CFG, LOG, str(target),
+                      precision=precision)
+        probs = model.classify_batch(x, lens, max_len=12048).cpu().numpy()
+        want = g[f"probs_{target}"]
+        d = np.abs(probs - want).max(axis=1)
+        worst[str(target)] = (float(d.max()), float(d.mean()))
+        assert d.max() < PROB_TOL[precision], (target, worst)
+        # decisions identical except where the reference p is within 1e-3 of the threshold
+        for thr in (0.9, 0.5, 0.99):
+            on_ref, on_got = want[:, 1] > np.float32(thr), probs[:, 1] > np.float32(thr)
+            near = np.abs(want[:, 1] - thr) <= 1e-3
+            assert np.all((on_ref == on_got) | near)
+    print("worst |dp| (max, mean):", worst)
+
+
+def test_classify_drop_in_and_short_input():
+    state = synth.state_dict(0)
+    model = Model(state, CFG, LOG, "mRNA")
+    assert model.target == "mRNA"
+    rng = np.random.default_rng(4)
+    y = pp.mad_normalise(synth.body(rng, 6000))
+    p = model.classify(y)                       # float64 ndarray in, Tensor[2] out (model.py:22-28)
+    p_off, p_on = p
+    want = net.classify(state, y)
+    assert abs(p_on.item() - want[1].item()) < 1e-3 and abs(p_off.item() + p_on.item() - 1) < 1e-6
+    assert bool(p_on > 0.9) == bool(want[1] > 0.9) or abs(want[1].item() - 0.9) < 1e-3
+    z = model.classify(np.zeros(5000, dtype=np.int64))      # MAD == 0 read: int64 zeros (preprocess.py:123)
+    assert abs(z[1].item() - net.classify(state, np.zeros(5000, dtype=np.int64))[1].item()) < 1e-3
+    with pytest.raises(RuntimeError):
+        model.classify(y[:4095])
+    with pytest.raises(RuntimeError):
+        Model({k: v for k, v in state.items() if k != "classifier.2.bias"}, CFG, LOG, "x")
+
+
+def test_fixed_batch_rna004_shapes():
+    """BASELINE config 2 shapes: fixed length 8,615 (reference-faithful) and 16,000 (as named)."""
+    state = synth.state_dict(0)
+    model = Model(state, CFG, LOG, "mRNA")
+    for L in (8615, 16000):
+        X = synth.body_batch(7, 6, L)
+        normed = [pp.mad_normalise(x) for x in X]
+        x, lens = to_device_batch(normed)
+        probs = model.classify_batch(x, lens, max_len=L).cpu().numpy()
+        want = net.classify_ragged(state, normed)
+        assert np.abs(probs - want).max() < 1e-3, (L, np.abs(probs - want).max())
+
+
+def test_decide_kernel_matches_control_rule():
+    rng = np.random.default_rng(8)
+    B, M = 600, 3
+    p_on = rng.random((M, B)).astype(np.float32)
+    p_on[:, :50] = np.float32(0.9)                   # exactly at threshold: strict '>' fails
+    p_on[:, 50:80] = np.nextafter(np.float32(0.9), np.float32(1))
+    probs = np.stack([1 - p_on, p_on], axis=2).astype(np.float32)
+    probs[0, 90:95] = np.nan
+    lens = rng.integers(4096, 12049, size=B).astype(np.int32)
+    lens[::7] = 12048
+    lens[5::11] = 0
+    for mode in ("enrich", "deplete"):
+        for thr in (0.9, 0.3, 0.5):
+            got = decide(torch.from_numpy(probs).cuda(), torch.from_numpy(lens).cuda(), thr, mode, 12048).cpu().numpy()
+            for b in range(B):
+                if lens[b] == 0:
+                    assert got[b] == ctl.SKIPPED
+                    continue
+                on = [torch.tensor(probs[m, b, 1]) for m in range(M)]
+                off = [torch.tensor(probs[m, b, 0]) for m in range(M)]
+                assert got[b] == ctl.decide(on, off, int(lens[b]), 12048, thr, mode), (mode, thr, b)
