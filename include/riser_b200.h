@@ -99,6 +99,16 @@ int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, in
                     int32_t* polya_end, int32_t* stats, int max_windows,
                     riser_stream_t stream);
 
+/* Replaces the length gating of riser/control.py:36-60 (with preprocess.py:84-85,
+ * 100, 104-106), batched: for read b of n[b] samples and poly(A) end `end` =
+ * cached_end[b] if >= 0 else detected_end[b] (-1 = none found):
+ *   found    : start = end + 1; skip if n - start < min_len; len = min(n - start, max_len)
+ *   not found: if n > fixed_trim + max_len  -> start = fixed_trim, len = max_len; else skip
+ * Skipped reads get len 0 (and start 0).                                          */
+int riser_select_window(const int32_t* n, const int32_t* cached_end, const int32_t* detected_end,
+                        int B, int min_len, int max_len, int fixed_trim, int32_t* start,
+                        int32_t* len, riser_stream_t stream);
+
 /* ------------------------------------------------------------------ network */
 
 typedef struct riser_model riser_model; /* packed weights of one ConvNet on one device */
@@ -138,6 +148,12 @@ int riser_plan_destroy(riser_plan* p);
  * feat (optional, may be NULL): fp32 [B, channels[n-1]] pooled features.       */
 int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len,
                   float* probs, float* feat, riser_stream_t stream);
+
+/* The three stages of riser_forward, callable separately so that a caller can put
+ * CUDA events between them (bench.py times the tensor-core stage alone):
+ * stage 0 = layer 0 (CUDA cores), 1 = conv layers 1..n-1 (tcgen05), 2 = head.   */
+int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
+                        const int32_t* len, float* probs, float* feat, riser_stream_t stream);
 
 /* Number of kernels one riser_forward launches (for gpu_launches accounting). */
 int riser_forward_launches(const riser_plan* p);

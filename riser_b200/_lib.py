@@ -21,6 +21,8 @@ SIGNATURES = {
     "riser_normalise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_i64,
                                 c_void_p, c_void_p]),
     "riser_polya_end": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "riser_select_window": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
     "riser_model_create": (c_int, [P(c_void_p), c_int, P(c_int), P(c_void_p), P(c_void_p), c_void_p,
                                    c_void_p, c_int, c_int]),
     "riser_model_destroy": (c_int, [c_void_p]),
@@ -28,6 +30,7 @@ SIGNATURES = {
     "riser_plan_create": (c_int, [P(c_void_p), c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "riser_plan_destroy": (c_int, [c_void_p]),
     "riser_forward": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "riser_forward_stage": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "riser_forward_launches": (c_int, [c_void_p]),
     "riser_plan_layer_info": (c_int, [c_void_p, c_int, P(c_i64), P(c_int), P(c_int), P(c_int), P(c_int)]),
     "riser_decide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),

@@ -992,14 +992,15 @@ extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset
   return RISER_OK;
 }
 
-extern "C" int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len, float* probs,
-                             float* feat, riser_stream_t stream) {
-  RISER_REQUIRE(p && x && len && probs, "riser_forward: null pointer");
-  RISER_REQUIRE(ld_x >= p->max_len && (ld_x & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
-                "riser_forward: x must be 8-byte aligned with even ld_x >= max_len");
+extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
+                                   const int32_t* len, float* probs, float* feat, riser_stream_t stream) {
+  RISER_REQUIRE(p && len, "riser_forward_stage: null pointer");
   const riser_model* m = p->model;
   cudaStream_t st = as_stream(stream);
-  {
+  if (stage == 0) {
+    RISER_REQUIRE(x, "riser_forward_stage: null x");
+    RISER_REQUIRE(ld_x >= p->max_len && (ld_x & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+                  "riser_forward: x must be 8-byte aligned with even ld_x >= max_len");
     const LayerPack& L = m->layer[0];
     const int64_t total = static_cast<int64_t>(p->B) * p->Lp[1] * (L.cout_p / 8);
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 32));
@@ -1007,22 +1008,36 @@ extern "C" int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, 
                                         reinterpret_cast<__half*>(p->ws + p->act_off[1]), p->B, p->Lp[1],
                                         L.cout, L.cout_p, m->act_planes);
     RISER_CUDA_TRY(cudaGetLastError());
-  }
-  for (int i = 1; i < m->n_layers; ++i) {
-    const LayerPlan& lp = p->layer[i];
-    ConvArgs a = lp.args;
-    a.len0 = len;
-    if (p->impl == 0)
-      conv_tc_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
-    else
-      conv_tc2_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
-    RISER_CUDA_TRY(cudaGetLastError());
-  }
-  {
+  } else if (stage == 1) {
+    for (int i = 1; i < m->n_layers; ++i) {
+      const LayerPlan& lp = p->layer[i];
+      ConvArgs a = lp.args;
+      a.len0 = len;
+      if (p->impl == 0)
+        conv_tc_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+      else
+        conv_tc2_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+      RISER_CUDA_TRY(cudaGetLastError());
+    }
+  } else if (stage == 2) {
+    RISER_REQUIRE(probs, "riser_forward_stage: null probs");
     const int n = m->n_layers;
     head_kernel<<<p->B, kHeadThreads, 0, st>>>(reinterpret_cast<const float*>(p->ws + p->act_off[n]), len, m->fc_w,
-                                      m->fc_b, probs, feat, p->B, p->Lp[n], m->layer[n - 1].cout_p, m->c_last, n);
+                                               m->fc_b, probs, feat, p->B, p->Lp[n], m->layer[n - 1].cout_p,
+                                               m->c_last, n);
     RISER_CUDA_TRY(cudaGetLastError());
+  } else {
+    return fail(RISER_EINVAL, "riser_forward_stage: stage %d outside 0..2", stage);
+  }
+  return RISER_OK;
+}
+
+extern "C" int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len, float* probs,
+                             float* feat, riser_stream_t stream) {
+  RISER_REQUIRE(p && x && len && probs, "riser_forward: null pointer");
+  for (int stage = 0; stage < 3; ++stage) {
+    const int st = riser_forward_stage(p, stage, x, ld_x, len, probs, feat, stream);
+    if (st) return st;
   }
   return RISER_OK;
 }

@@ -399,6 +399,30 @@ polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
   }
 }
 
+// riser/control.py:36-60 length gating
+__global__ void select_window_kernel(const int32_t* __restrict__ n, const int32_t* __restrict__ cached,
+                                     const int32_t* __restrict__ detected, int B, int min_len, int max_len,
+                                     int fixed_trim, int32_t* __restrict__ start, int32_t* __restrict__ len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int nb = n[b];
+  int end = cached ? cached[b] : -1;
+  if (end < 0 && detected) end = detected[b];
+  int st = 0, ln = 0;
+  if (end > 0) {                               // Python truthiness: 0 / None = not found
+    const int avail = nb - (end + 1);
+    if (avail >= min_len) {
+      st = end + 1;
+      ln = min(avail, max_len);
+    }
+  } else if (nb > fixed_trim + max_len) {      // preprocess.py:84-85 (strict)
+    st = fixed_trim;
+    ln = max_len;
+  }
+  start[b] = st;
+  len[b] = ln;
+}
+
 int g_sm_count = 0;
 int sm_count() {
   if (g_sm_count == 0) {
@@ -453,6 +477,18 @@ extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int
   const int grid = std::min(B, sm_count() * per_sm);
   normalise_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, start, len, B, out, ld_out,
                                                                med2_mad4);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+extern "C" int riser_select_window(const int32_t* n, const int32_t* cached_end, const int32_t* detected_end,
+                                   int B, int min_len, int max_len, int fixed_trim, int32_t* start,
+                                   int32_t* len, riser_stream_t stream) {
+  RISER_REQUIRE(B >= 0, "riser_select_window: B < 0");
+  if (B == 0) return RISER_OK;
+  RISER_REQUIRE(n && start && len, "riser_select_window: null pointer");
+  select_window_kernel<<<(B + 255) / 256, 256, 0, as_stream(stream)>>>(n, cached_end, detected_end, B, min_len,
+                                                                     max_len, fixed_trim, start, len);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

@@ -19,6 +19,7 @@ PREC_F16_W2 = 1    # two passes, weights split hi + lo (exact to ~22 bits)
 PREC_F16_X3 = 2    # three passes, weights and activations split hi + lo: fp32-class
 DEFAULT_PRECISION = PREC_F16_X3
 MIN_LENGTH = 4096  # riser/preprocess.py:8 -- 12 stride-2 pools
+DEFAULT_CHUNK = 256  # reads per network sub-batch (activations of one sub-batch fit the L2)
 
 
 class Plan:
@@ -159,19 +160,47 @@ class Model():
         lens = torch.tensor([n], dtype=torch.int32, device=self.device)
         return self.classify_batch(x, lens, max_len=ld)[0]
 
-    def classify_batch(self, x, lens, max_len=None, probs=None, feat=None):
+    def classify_batch(self, x, lens, max_len=None, probs=None, feat=None, chunk=None, events=None):
         """x: fp32 [B, ld] normalised signals on the device (8-byte aligned rows, even
         ld), lens: int32 [B] valid lengths (>= 4096; shorter -> NaN row).
-        Returns probs fp32 [B, 2] on the device.  No synchronisation."""
+        Returns probs fp32 [B, 2] on the device.  No synchronisation.
+
+        chunk: run the network over sub-batches of this many reads so that the
+        inter-layer activations of one sub-batch stay resident in the 126 MB L2
+        (default: DEFAULT_CHUNK when B is larger).
+        events: optional list; (start, end) torch.cuda.Event pairs bracketing the
+        tcgen05 conv stage of every sub-batch are appended (bench.py's roofline)."""
         B = x.shape[0]
         max_len = int(max_len if max_len is not None else x.shape[1])
-        p = self.plan(B, max_len)
         if probs is None:
             probs = torch.empty(B, 2, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().riser_forward(p._handle, _lib.ptr(x), x.stride(0), _lib.ptr(lens),
-                                            _lib.ptr(probs), _lib.ptr(feat), _lib.stream_ptr()),
-                   "riser_forward")
+        chunk = int(chunk or DEFAULT_CHUNK)
+        L = _lib.lib()
+        stream = _lib.stream_ptr()
+        for lo in range(0, B, chunk):
+            n = min(chunk, B - lo)
+            p = self.plan(n, max_len)
+            xs, ls, ps = x[lo:lo + n], lens[lo:lo + n], probs[lo:lo + n]
+            fs = None if feat is None else feat[lo:lo + n]
+            if events is None:
+                _lib.check(L.riser_forward(p._handle, _lib.ptr(xs), x.stride(0), _lib.ptr(ls), _lib.ptr(ps),
+                                           _lib.ptr(fs), stream), "riser_forward")
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for stage in range(3):
+                if stage == 1:
+                    e0.record()
+                _lib.check(L.riser_forward_stage(p._handle, stage, _lib.ptr(xs), x.stride(0), _lib.ptr(ls),
+                                                 _lib.ptr(ps), _lib.ptr(fs), stream), "riser_forward_stage")
+                if stage == 1:
+                    e1.record()
+            events.append((e0, e1))
         return probs
+
+    def launches(self, B, max_len, chunk=None):
+        """Kernels one classify_batch call launches."""
+        chunk = int(chunk or DEFAULT_CHUNK)
+        return sum(self.plan(min(chunk, B - lo), max_len).launches for lo in range(0, B, chunk))
 
 
 def decide(probs, lens, threshold, mode, max_len):

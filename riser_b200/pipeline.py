@@ -1,0 +1,136 @@
+"""Batched trim -> normalise -> classify -> decide pipeline: the additive surface the
+rewritten ReadUntil loop calls once per ``get_read_batch()``, replacing
+the serial per-read body of riser/control.py:31-93.
+
+Everything between the H2D copy of the packed int16 signals and the D2H copy of the
+decision bytes / probabilities runs in the sm_100a kernels behind the C ABI, on the
+current CUDA stream, with one host synchronisation per batch.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .preprocess import RaggedBatch
+from .model import decide, DEFAULT_CHUNK
+
+# decision codes (include/riser_b200.h)
+TRY_AGAIN, ACCEPT, REJECT, NO_DECISION, SKIPPED = 0, 1, 2, 3, 4
+DECISION_NAMES = {TRY_AGAIN: "try_again", ACCEPT: "accept", REJECT: "reject",
+                  NO_DECISION: "no_decision", SKIPPED: "skipped"}
+
+
+class BatchResult:
+    """Host-side result of one batch: ``decisions`` uint8 [B], ``p_on`` / ``p_off``
+    float32 [B, M], ``sig_len`` int32 [B] (post-trim window length, 0 = skipped),
+    ``polya_end`` int32 [B] (-1 = none)."""
+    __slots__ = ("decisions", "p_on", "p_off", "sig_len", "polya_end", "h2d_bytes", "d2h_bytes")
+
+
+class BatchedClassifier:
+    def __init__(self, models, processor, chunk=None):
+        self.models = list(models)
+        self.proc = processor
+        self.device = _lib.require_device()
+        self.chunk = int(chunk or DEFAULT_CHUNK)
+        self.min_len = processor.get_min_length()
+        self.max_len = processor.get_max_length()
+        self.fixed_trim = processor.get_fixed_trim_length()
+        self.ld = (self.max_len + 3) & ~3
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ device stages
+    def _buffers(self, B):
+        b = self._bufs.get(B)
+        if b is None:
+            dev, M = self.device, len(self.models)
+            b = self._bufs[B] = {
+                "x": torch.zeros(B, self.ld, dtype=torch.float32, device=dev),
+                "start": torch.zeros(B, dtype=torch.int32, device=dev),
+                "len": torch.zeros(B, dtype=torch.int32, device=dev),
+                "probs": torch.zeros(M, B, 2, dtype=torch.float32, device=dev),
+                "detected": torch.full((B,), -1, dtype=torch.int32, device=dev),
+                "out_host": torch.empty(B * (1 + 4 + 4 + 8 * M), dtype=torch.uint8).pin_memory(),
+            }
+        return b
+
+    def run_windows(self, batch, start, length, threshold, mode, events=None):
+        """normalise + classify (every model) + decide for windows already chosen.
+        batch: RaggedBatch; start / length: int32 device tensors [B] (length 0 = skip).
+        Returns (decisions uint8 [B], probs fp32 [M, B, 2]) on the device."""
+        B = batch.B
+        buf = self._buffers(B)
+        L = _lib.lib()
+        _lib.check(L.riser_normalise(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(start), _lib.ptr(length),
+                                     B, self.max_len, _lib.ptr(buf["x"]), buf["x"].stride(0), None,
+                                     _lib.stream_ptr()), "riser_normalise")
+        for m, model in enumerate(self.models):
+            model.classify_batch(buf["x"], length, max_len=self.max_len, probs=buf["probs"][m],
+                                 chunk=self.chunk, events=events)
+        decisions = decide(buf["probs"], length, threshold, mode, self.max_len)
+        return decisions, buf["probs"]
+
+    def select_windows(self, batch, cached_end):
+        """poly(A) detection for reads without a cached end + control.py:36-60 gating.
+        cached_end: int32 host array [B] (-1 = not cached).  Device tensors out."""
+        B = batch.B
+        buf = self._buffers(B)
+        L = _lib.lib()
+        cached = torch.from_numpy(np.ascontiguousarray(cached_end, dtype=np.int32)).to(self.device, non_blocking=True)
+        # detection is only needed where nothing is cached; reads with a cache hit keep -1
+        # (their prefix is skipped by giving them length 0 in the detection launch)
+        n_detect = torch.where(cached >= 0, torch.zeros_like(batch.n), batch.n)
+        _lib.check(L.riser_polya_end(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(n_detect), B,
+                                     _lib.ptr(buf["detected"]), None, 0, _lib.stream_ptr()), "riser_polya_end")
+        _lib.check(L.riser_select_window(_lib.ptr(batch.n), _lib.ptr(cached), _lib.ptr(buf["detected"]), B,
+                                         self.min_len, self.max_len, self.fixed_trim, _lib.ptr(buf["start"]),
+                                         _lib.ptr(buf["len"]), _lib.stream_ptr()), "riser_select_window")
+        return buf["start"], buf["len"], buf["detected"]
+
+    # ------------------------------------------------------------------ public entry
+    def classify_batch(self, signals, read_ids, polyA_cache, threshold, mode):
+        """One pass of riser/control.py:31-97 over a batch.
+
+        signals: list of int16 arrays (the whole accumulated prefix of each read, as
+        ``client.get_raw_signal`` returns it); read_ids: matching ids; polyA_cache: the
+        loop's dict (updated here exactly as control.py does: found ends are stored, and
+        the dict is cleared when it reaches 1000 entries after an assessed read).
+        Returns a BatchResult with host arrays."""
+        B = len(signals)
+        res = BatchResult()
+        M = len(self.models)
+        if B == 0:
+            res.decisions = np.zeros(0, np.uint8)
+            res.p_on = res.p_off = np.zeros((0, M), np.float32)
+            res.sig_len = res.polya_end = np.zeros(0, np.int32)
+            res.h2d_bytes = res.d2h_bytes = 0
+            return res
+        cached = np.fromiter((polyA_cache.get(r, -1) for r in read_ids), dtype=np.int32, count=B)
+        batch = RaggedBatch(signals, self.device)
+        start, length, detected = self.select_windows(batch, cached)
+        decisions, probs = self.run_windows(batch, start, length, threshold, mode)
+        # packed pinned result buffer: len | detected | probs | decisions (4-byte fields first)
+        buf = self._buffers(B)
+        host = buf["out_host"]
+        o0, o1, o2 = 4 * B, 8 * B, 8 * B + 8 * M * B
+        host[:o0].view(torch.int32).copy_(length, non_blocking=True)
+        host[o0:o1].view(torch.int32).copy_(detected, non_blocking=True)
+        host[o1:o2].view(torch.float32).view(M, B, 2).copy_(probs, non_blocking=True)
+        host[o2:].copy_(decisions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hv = host.numpy()
+        res.sig_len = hv[:o0].view(np.int32).copy()
+        det = hv[o0:o1].view(np.int32).copy()
+        pr = hv[o1:o2].view(np.float32).reshape(M, B, 2)
+        res.decisions = hv[o2:].copy()
+        res.p_off = np.ascontiguousarray(pr[:, :, 0].T)
+        res.p_on = np.ascontiguousarray(pr[:, :, 1].T)
+        res.polya_end = np.where(cached >= 0, cached, det)
+        res.h2d_bytes = batch.h2d_bytes + cached.nbytes
+        res.d2h_bytes = host.numel()
+        # cache bookkeeping in read order (preprocess.py:93-98, control.py:96-97)
+        for r in range(B):
+            if cached[r] < 0 and det[r] > 0:
+                polyA_cache[read_ids[r]] = int(det[r])
+            if res.decisions[r] != SKIPPED and len(polyA_cache) >= 1000:
+                polyA_cache.clear()
+        return res

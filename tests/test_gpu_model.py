@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from oracle import preprocess_oracle as pp
 from oracle import convnet_oracle as net
 from oracle import control_oracle as ctl
-from oracle.refshim import AttrDict
+from riser_b200.config import AttrDict
 from riser_b200 import Model, decide, synth, PREC_F16, PREC_F16_W2, PREC_F16_X3
 from tests.golden import make_golden_params as P
 

@@ -1,0 +1,93 @@
+"""GPU: the batched pipeline and the drop-in SequencerControl against (a) the rows the
+REFERENCE's own SequencerControl.target wrote for the same simulated run (golden) and
+(b) the oracle's serial restatement of control.py:31-97 on ragged raw reads."""
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from oracle import control_oracle as ctl
+from riser_b200.config import AttrDict
+from riser_b200 import (Kit, SignalProcessor, Model, BatchedClassifier, SequencerControl, synth, sim)
+from tests.golden import make_golden_params as P
+
+pytestmark = pytest.mark.gpu
+LOG = logging.getLogger("test")
+CFG = AttrDict({"cnn": {"n_layers": 12, "depth": 1, "channels": synth.CHANNELS, "kernels": [3] * 12,
+                        "n_classes": 2, "classifier": "gap_fc"}})
+
+
+def models_for(targets):
+    return [Model(synth.state_dict(synth.TARGET_SEEDS[t]), CFG, LOG, t) for t in targets]
+
+
+@pytest.mark.parametrize("mode", ["deplete", "enrich"])
+def test_control_loop_reproduces_reference_run(golden_dir, tmp_path, mode):
+    g = np.load(os.path.join(golden_dir, "control_scenario.npz"))
+    reads = P.scenario_reads()
+    client = sim.SimClient(reads, int(g["chunk"]), int(g["n_polls"]), first_len=int(g["first_len"]))
+    proc = SignalProcessor(Kit.create_from_version(str(g["kit"])))
+    control = SequencerControl(client, models_for([str(t) for t in g["targets"]]), proc, LOG,
+                               str(tmp_path / f"run_{mode}"))
+    control.start()
+    control.target(mode, 1, float(g["threshold"]))
+    control.finish()
+    with open(tmp_path / f"run_{mode}.csv") as f:
+        lines = [ln.rstrip("\n") for ln in f]
+    assert lines[0] == str(g["header"])
+    got = [ln.split(",", 1)[1].split(",") for ln in lines[1:]]
+    want = [r.split(",") for r in g[f"rows_{mode}"]]
+    assert len(got) == len(want)
+    thr = float(g["threshold"])
+    for a, b in zip(got, want):
+        assert a[:4] == b[:4], (a, b)                      # read id, channel, sig_length, models
+        pa = np.array([float(x) for x in a[4].split(";")])
+        pb = np.array([float(x) for x in b[4].split(";")])
+        assert np.abs(pa - pb).max() < 1e-3
+        assert a[5:7] == b[5:7]                            # threshold, mode
+        assert a[7] == b[7] or np.abs(pb - thr).min() <= 1e-3
+    assert sorted(map(tuple, g[f"unblocked_{mode}"])) == sorted(client.unblocked)
+    assert sorted(map(tuple, g[f"finished_{mode}"])) == sorted(client.finished)
+    assert client.messages and len(control.batch_latencies) == int(g["n_polls"])
+
+
+def test_batched_pipeline_vs_oracle_serial_loop():
+    """Ragged raw prefixes, three targets, fused trim + normalise + classify + decide
+    (BASELINE config 3 shape) against the oracle's serial per-read loop."""
+    reads = synth.raw_reads(5, 64, min_body=3000, max_body=16000, frac_no_polya=0.2, frac_const=0.05)
+    # truncate to varied prefixes so every branch of control.py:36-60 is taken
+    rng = np.random.default_rng(1)
+    items = [(rid, sig[:int(rng.integers(len(sig) // 2, len(sig) + 1))]) for rid, sig in reads]
+    targets = ["mRNA", "mtRNA", "globin"]
+    states = [synth.state_dict(synth.TARGET_SEEDS[t]) for t in targets]
+    proc = SignalProcessor(Kit.create_from_version("RNA002"))
+    clf = BatchedClassifier(models_for(targets), proc)
+    for mode in ("deplete", "enrich"):
+        cache_o, cache_g = {}, {}
+        dec_o, p_on_o, p_off_o, len_o, cache_o = ctl.run_batch(items, states, "RNA002", cache_o, 0.9, mode)
+        res = clf.classify_batch([s for _, s in items], [r for r, _ in items], cache_g, 0.9, mode)
+        assert np.array_equal(res.sig_len, len_o)
+        assert cache_g == cache_o
+        assessed = len_o > 0
+        assert assessed.sum() > 10 and (~assessed).sum() > 3
+        assert np.abs(res.p_on[assessed] - p_on_o[assessed]).max() < 1e-3
+        assert np.abs(res.p_off[assessed] - p_off_o[assessed]).max() < 1e-3
+        near = (np.abs(p_on_o - 0.9).min(axis=1) <= 1e-3) | (np.abs(p_off_o - 0.9).min(axis=1) <= 1e-3)
+        assert np.all((res.decisions == dec_o) | near)
+        assert (res.decisions == dec_o).mean() >= 0.999 or near.any()
+        # a second pass hits the cache for every read whose poly(A) was found
+        res2 = clf.classify_batch([s for _, s in items], [r for r, _ in items], cache_g, 0.9, mode)
+        assert np.array_equal(res2.decisions, res.decisions) and np.array_equal(res2.sig_len, res.sig_len)
+
+
+def test_rna004_kit_and_empty_batch():
+    proc = SignalProcessor(Kit.create_from_version("RNA004"))
+    clf = BatchedClassifier(models_for(["mRNA"]), proc)
+    assert (clf.max_len, clf.fixed_trim) == (8615, 4633)
+    res = clf.classify_batch([], [], {}, 0.9, "deplete")
+    assert res.decisions.shape == (0,)
+    reads = synth.raw_reads(9, 12, min_body=9000, max_body=14000)
+    res = clf.classify_batch([s for _, s in reads], [r for r, _ in reads], {}, 0.9, "deplete")
+    dec_o, p_on_o, _, len_o, _ = ctl.run_batch(reads, [synth.state_dict(0)], "RNA004", {}, 0.9, "deplete")
+    assert np.array_equal(res.sig_len, len_o) and np.abs(res.p_on - p_on_o).max() < 1e-3

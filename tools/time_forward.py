@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from oracle.refshim import AttrDict            # noqa: E402  (config holder only)
+from riser_b200.config import AttrDict           # noqa: E402
 from riser_b200 import Model, SignalProcessor, Kit, RaggedBatch, synth   # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
