@@ -260,6 +260,8 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / args.steps
+    # the bracket covers layer 0 (CUDA cores) + conv layers 1..11; take layer 0's launches out
+    conv_ms -= mdl.time_layer0(clf._buffers(B)["x"], length, L)
     # ---- e2e: host int16 -> H2D -> pipeline -> D2H decisions + probs, wall clock per step on the device stream
     dec_host = torch.empty(B, dtype=torch.uint8).pin_memory()
     probs_host = torch.empty(1, B, 2, dtype=torch.float32).pin_memory()

@@ -149,9 +149,12 @@ int riser_plan_destroy(riser_plan* p);
 int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len,
                   float* probs, float* feat, riser_stream_t stream);
 
-/* The three stages of riser_forward, callable separately so that a caller can put
- * CUDA events between them (bench.py times the tensor-core stage alone):
- * stage 0 = layer 0 (CUDA cores), 1 = conv layers 1..n-1 (tcgen05), 2 = head.   */
+/* The stages of riser_forward, callable separately so that a caller can put CUDA
+ * events between them (bench.py times the conv stack):
+ *   0 = layer 0 (CUDA cores) + the memory-bound early conv layers, run chunk of reads by
+ *       chunk of reads so their activations stay in the L2;
+ *   1 = the remaining conv layers over the whole batch (tcgen05);  2 = head;
+ *   3 = the layer-0 launches of stage 0 alone (timing aid, not part of riser_forward). */
 int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
                         const int32_t* len, float* probs, float* feat, riser_stream_t stream);
 

@@ -34,10 +34,7 @@ constexpr int kBlockM = 128;          // rows per tile (UMMA M)
 constexpr int kBlockK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
 constexpr int kMaxNTile = 256;        // UMMA N limit
 constexpr int kTmemCols = 512;        // two accumulator buffers of up to 256 columns
-constexpr int kConvThreads = 192;     // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue
 constexpr int kMinLen = 4096;         // riser/preprocess.py:8
-constexpr int kDefaultConvImpl = 1;   // see riser_plan_create
-constexpr int kMaxStages = 12;        // operand ring depth (deep: early layers are latency bound)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -89,23 +86,25 @@ struct ConvArgs {
   const int32_t* len0;
   void* out;
   int rows_in, Lp_in, Lp_out, shift;
-  int cin_p, cout_p, n_tile, n_tiles, m_tiles, k_blocks, passes, stages, out_fp32;
+  int cin_p, cout_p, n_tile, n_tiles, k_blocks;
+  int super0, n_supers;   // range of M super-tiles this launch covers (x n_tiles work items)
+  int ms;                 // 128-row M sub-tiles per work item (they share every weight tile)
+  int planes;             // activation planes read (1, or 2 = hi + lo)
+  int wplanes;            // weight planes (1, or 2 = hi + lo)
+  int out_planes, out_fp32;
+  int a_stages, b_stages, acc_stages, resident;
+  int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
+  int half_lp;            // Lp_in / 2
+  int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x 128)
+  unsigned long long pair_magic;   // floor(2^40 / half_lp) + 1: pair index -> read index
   uint32_t idesc;
-  // v2 kernel (single A load per K block, shifted descriptors per tap)
-  int n_asteps;          // A loads per K block: 1, or 2 when the activation lo plane is used
-  int a_plane[2];        // activation plane (0 = hi, 1 = lo) of each A step
-  int n_w[2];            // weight planes multiplied against each A step
-  int w_plane[2][2];
-  int n_wplanes;         // weight planes resident / in the tensor
-  int out_planes;        // 1, or 2 = write hi and lo fp16 planes
-  int a_stages, b_stages, resident, base_off_mode;
   float w_inv_scale;
 };
 
 struct LayerPlan {
   CUtensorMap tm_a, tm_b;
   ConvArgs args;
-  int grid = 0;
+  int n_supers_total = 0;
   size_t smem = 0;
 };
 
@@ -114,7 +113,8 @@ struct LayerPlan {
 
 struct riser_plan {
   const riser_model* model = nullptr;
-  int B = 0, max_len = 0, impl = 0;
+  int B = 0, max_len = 0;
+  int chunk_reads = 0, n_chunked = 0;   // early layers 0..n_chunked-1 run chunk by chunk (L2 residency)
   int Lmax[riser::kMaxLayers + 1];
   int Lp[riser::kMaxLayers + 1];
   size_t act_off[riser::kMaxLayers + 1];
@@ -179,11 +179,27 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
 
 // ------------------------------------------------------------------------------------
 // tcgen05 implicit-GEMM convolution with fused bias + ReLU + MaxPool(2,2) + length mask.
+//
+// Work item = (M super-tile of `ms` x 128 flat rows, N tile).  Per 64-channel K block the
+// producer loads, for every sub-tile and activation plane, ONE 130-row A tile (the 128 rows
+// plus a halo row on each side); the three taps read it through descriptors whose start
+// address is shifted by 0 / 1 / 2 rows (the 128-byte swizzle is a function of the absolute
+// shared-memory address, so a row shift keeps TMA's and the MMA's views consistent).
+// Weight tiles are either resident in shared memory for the whole kernel (one N tile and
+// all taps fit: the early layers) or streamed through their own ring, each loaded tile
+// being used by every sub-tile and plane before it is released.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = two epilogue
+// sets (each covers the four TMEM lane quadrants; the sets split the 16-column chunks).
+constexpr int kATileBytes = 136 * 128;      // smem stride of one A tile, multiple of 1024
+constexpr int kMaxAStages = 8, kMaxBStages = 8, kMaxAccStages = 4;
+constexpr int kConvThreads = 320;
+constexpr int kEpiThreads = 256;
+
 struct ConvSmem {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  uint64_t w_full;
+  uint64_t tmem_full[kMaxAccStages], tmem_empty[kMaxAccStages];
   uint32_t tmem_base;
   float bias[2][kMaxNTile];
 };
@@ -193,242 +209,86 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Epilogue for one chunk of W (= 32 or 16) accumulator columns held one row per lane.
-// Rows (lanes) 2j and 2j+1 are the two positions of one max-pool pair; lane parity picks
-// which half of the chunk's columns this lane finishes and stores.
-template <int W>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* bias_s, int col0,
-                                               bool odd, bool valid, bool writable, void* out_row,
-                                               bool out_fp32, int lo_plane_off = 0, float inv_scale = 1.f) {
-  constexpr int H = W / 2;
-  float r[H];
+// Epilogue for one chunk of 16 accumulator columns held one row per lane.  Rows (lanes) 2j
+// and 2j+1 are the two positions of one max-pool pair; the even lane finishes and stores
+// columns 0..7 of the chunk, the odd lane columns 8..15.
+__device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const float* bias_s, int col0,
+                                                 bool odd, bool valid, bool writable, void* out_row,
+                                                 bool out_fp32, int lo_plane_off, float inv_scale) {
+  float r[8];
 #pragma unroll
-  for (int j = 0; j < H; ++j) {
-    const float mine = __uint_as_float(odd ? v[j + H] : v[j]);
-    const float send = __uint_as_float(odd ? v[j] : v[j + H]);
+  for (int j = 0; j < 8; ++j) {
+    const float mine = __uint_as_float(odd ? v[j + 8] : v[j]);
+    const float send = __uint_as_float(odd ? v[j] : v[j + 8]);
     const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    const float bsum = fmaf(fmaxf(mine, recv), inv_scale, bias_s[col0 + (odd ? H : 0) + j]);
+    const float bsum = fmaf(fmaxf(mine, recv), inv_scale, bias_s[col0 + (odd ? 8 : 0) + j]);
     r[j] = valid ? fmaxf(bsum, 0.f) : 0.f;
   }
   if (!writable) return;
-  const int c = col0 + (odd ? H : 0);
+  const int c = col0 + (odd ? 8 : 0);
   if (out_fp32) {
     float4* o = reinterpret_cast<float4*>(static_cast<float*>(out_row) + c);
-#pragma unroll
-    for (int j = 0; j < H / 4; ++j) o[j] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    o[0] = make_float4(r[0], r[1], r[2], r[3]);
+    o[1] = make_float4(r[4], r[5], r[6], r[7]);
   } else {
-    uint4* o = reinterpret_cast<uint4*>(static_cast<__half*>(out_row) + c);
+    __half* oh = static_cast<__half*>(out_row) + c;
+    *reinterpret_cast<uint4*>(oh) =
+        make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
+    if (lo_plane_off) {   // residual plane: a = hi + lo, hi = fp16(a), lo = fp16(a - hi)
 #pragma unroll
-    for (int j = 0; j < H / 8; ++j)
-      o[j] = make_uint4(pack_half2(r[8 * j], r[8 * j + 1]), pack_half2(r[8 * j + 2], r[8 * j + 3]),
-                        pack_half2(r[8 * j + 4], r[8 * j + 5]), pack_half2(r[8 * j + 6], r[8 * j + 7]));
-    if (lo_plane_off) {   // residual plane: a = hi + lo with hi = fp16(a), lo = fp16(a - hi)
-#pragma unroll
-      for (int j = 0; j < H; ++j) r[j] -= __half2float(__float2half_rn(fminf(r[j], 65504.f)));
-      uint4* ol = reinterpret_cast<uint4*>(static_cast<__half*>(out_row) + lo_plane_off + c);
-#pragma unroll
-      for (int j = 0; j < H / 8; ++j)
-        ol[j] = make_uint4(pack_half2(r[8 * j], r[8 * j + 1]), pack_half2(r[8 * j + 2], r[8 * j + 3]),
-                           pack_half2(r[8 * j + 4], r[8 * j + 5]), pack_half2(r[8 * j + 6], r[8 * j + 7]));
+      for (int j = 0; j < 8; ++j) r[j] -= __half2float(__float2half_rn(fminf(r[j], 65504.f)));
+      *reinterpret_cast<uint4*>(oh + lo_plane_off) =
+          make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
     }
   }
 }
 
+// Descriptor for a K-major SWIZZLE_128B tile at shared address `addr` (< 256 KB).
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
+  constexpr uint64_t kHi = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                           (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+  return kHi | static_cast<uint64_t>(addr >> 4);
+}
+
+// Work items are numbered with the N tile fastest; a CTA visits item, item + grid, ...
+// Decoding is kept incremental (no division in the single-thread roles' loops).
+struct ItemCursor {
+  int super, n, step_super, step_n, n_tiles;
+  __device__ __forceinline__ ItemCursor(int first, int grid, int n_tiles_, int super0) : n_tiles(n_tiles_) {
+    super = super0 + first / n_tiles_;
+    n = first % n_tiles_;
+    step_super = grid / n_tiles_;
+    step_n = grid % n_tiles_;
+  }
+  __device__ __forceinline__ void next() {
+    super += step_super;
+    n += step_n;
+    if (n >= n_tiles) {
+      n -= n_tiles;
+      ++super;
+    }
+  }
+};
+
+template <int MS, int PLANES, int WPLANES, bool RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
-  // operand ring first (1024-byte aligned for SWIZZLE_128B), bookkeeping after it
   unsigned char* base = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t a_bytes = kBlockM * kBlockK * 2;
-  const uint32_t b_bytes = a.n_tile * kBlockK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  ConvSmem& s = *reinterpret_cast<ConvSmem*>(base + static_cast<size_t>(a.stages) * stage_bytes);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_tiles_total = a.m_tiles * a.n_tiles;
-  const int k_iters = a.passes * 3 * a.k_blocks;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
-    for (int i = 0; i < a.stages; ++i) {
-      mbar_init(&s.full[i], 1);
-      mbar_init(&s.empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(&s.tmem_base, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = s.tmem_base;
-
-  if (warp == 0) {
-    // ===================== TMA producer (one elected lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int m0 = (tile / a.n_tiles) * kBlockM;
-        const int n0 = (tile % a.n_tiles) * a.n_tile;
-        for (int pass = 0; pass < a.passes; ++pass) {
-          for (int tap = 0; tap < 3; ++tap) {
-            for (int kb = 0; kb < a.k_blocks; ++kb) {
-              mbar_wait(&s.empty[stage], phase ^ 1);
-              unsigned char* sa = base + static_cast<size_t>(stage) * stage_bytes;
-              mbar_arrive_expect_tx(&s.full[stage], stage_bytes);
-              tma_load_2d(sa, &tm_a, &s.full[stage], kb * kBlockK, m0 + tap - 1);
-              tma_load_2d(sa + a_bytes, &tm_b, &s.full[stage], kb * kBlockK,
-                          (pass * 3 + tap) * a.cout_p + n0);
-              if (++stage == a.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kMaxNTile;
-        int kb = 0;
-        for (int ki = 0; ki < k_iters; ++ki) {
-          mbar_wait(&s.full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(base + static_cast<size_t>(stage) * stage_bytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + a_bytes);
-          const int nk = min(kBlockK / 16, (a.cin_p - kb * kBlockK) / 16);
-          for (int k = 0; k < nk; ++k)
-            umma_f16(d_tmem, da + 2 * k, db + 2 * k, a.idesc, (ki | k) != 0);
-          umma_commit(&s.empty[stage]);            // smem slot free once these MMAs have read it
-          if (ki == k_iters - 1) umma_commit(&s.tmem_full[acc]);
-          if (++kb == a.k_blocks) kb = 0;
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue warps 2..5 =====================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int et = threadIdx.x - 64;        // 0..127
-    const bool odd = lane & 1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / a.n_tiles) * kBlockM;
-      const int n0 = (tile % a.n_tiles) * a.n_tile;
-      // stage this tile's bias slice (double buffered by acc; the barrier below orders it)
-      for (int i = et; i < a.n_tile; i += 128) s.bias[acc][i] = a.bias[n0 + i];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-
-      const int r_even = (m0 + 32 * q + lane) & ~1;
-      bool valid = false, writable = false;
-      int64_t out_row = 0;
-      if (r_even < a.rows_in) {
-        const int b = r_even / a.Lp_in;
-        const int tp = (r_even - b * a.Lp_in) >> 1;
-        valid = tp < (a.len0[b] >> a.shift);
-        writable = tp < a.Lp_out;
-        out_row = static_cast<int64_t>(b) * a.Lp_out + tp;
-      }
-      void* orow = a.out_fp32
-                       ? static_cast<void*>(static_cast<float*>(a.out) + out_row * a.cout_p + n0)
-                       : static_cast<void*>(static_cast<__half*>(a.out) + out_row * a.cout_p + n0);
-
-      mbar_wait(&s.tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * kMaxNTile;
-      int col = 0;
-      for (; col + 32 <= a.n_tile; col += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + col, v);
-        tmem_ld_wait();
-        epilogue_chunk<32>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, 0, a.w_inv_scale);
-      }
-      if (col < a.n_tile) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_addr + col, v);
-        tmem_ld_wait();
-        epilogue_chunk<16>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, 0, a.w_inv_scale);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// v2: one A load per K block (130 rows: the 128-row tile plus one halo row on each side);
-// the three taps read it through descriptors whose start address is shifted by 0/1/2 rows.
-// Weights are either resident in shared memory for the whole kernel (layers whose three
-// taps fit: one N tile) or streamed through their own ring.
-constexpr int kARows = kBlockM + 2;
-constexpr int kAStageBytes = 136 * 128;     // ring stride, multiple of 1024
-constexpr int kATxBytes = kARows * 128;
-constexpr int kMaxAStages = 8, kMaxBStages = 8;
-
-struct ConvSmem2 {
-  uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
-  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
-  uint64_t w_full;
-  uint64_t tmem_full[2], tmem_empty[2];
-  uint32_t tmem_base;
-  float bias[2][kMaxNTile];
-};
-
-__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t smem_addr, uint32_t base_offset) {
-  return umma_desc_sw128(smem_addr) | (static_cast<uint64_t>(base_offset & 7) << 49);
-}
-
-__global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const ConvArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int kATiles = MS * PLANES;                       // A tiles per K block
+  constexpr uint32_t kAGroupBytes = kATiles * kATileBytes;
   const uint32_t b_bytes = a.n_tile * kBlockK * 2;
   unsigned char* a_ring = base;
-  unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAStageBytes;
-  const size_t b_region_bytes = a.resident ? static_cast<size_t>(a.n_wplanes) * 3 * a.k_blocks * b_bytes
-                                           : static_cast<size_t>(a.b_stages) * b_bytes;
-  ConvSmem2& s = *reinterpret_cast<ConvSmem2*>(b_region + b_region_bytes);
+  unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroupBytes;
+  const size_t b_region_bytes = RESIDENT ? static_cast<size_t>(WPLANES) * 3 * a.k_blocks * b_bytes
+                                         : static_cast<size_t>(a.b_stages) * b_bytes;
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + b_region_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tiles_total = a.m_tiles * a.n_tiles;
+  const int n_items = a.n_supers * a.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -442,9 +302,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&s.b_empty[i], 1);
     }
     mbar_init(&s.w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < a.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], 4);
+      mbar_init(&s.tmem_empty[i], kEpiThreads / 32);
     }
     fence_mbar_init();
   }
@@ -460,9 +320,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (a.resident) {
+      if (RESIDENT) {
         mbar_arrive_expect_tx(&s.w_full, static_cast<uint32_t>(b_region_bytes));
-        for (int wp = 0; wp < a.n_wplanes; ++wp)
+        for (int wp = 0; wp < WPLANES; ++wp)
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < a.k_blocks; ++kb)
               tma_load_2d(b_region + static_cast<size_t>((wp * 3 + tap) * a.k_blocks + kb) * b_bytes, &tm_b,
@@ -470,32 +330,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int m0 = (tile / a.n_tiles) * kBlockM;
-        const int n0 = (tile % a.n_tiles) * a.n_tile;
+      const uint32_t a_tx = kATiles * a.a_tx_bytes;
+      ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+        const int m0 = cur.super * (MS * kBlockM) - 1;
+        const int n0 = cur.n * a.n_tile;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
-          for (int as = 0; as < a.n_asteps; ++as) {
-            mbar_wait(&s.a_empty[sa], pa ^ 1);
-            mbar_arrive_expect_tx(&s.a_full[sa], kATxBytes);
-            tma_load_2d(a_ring + static_cast<size_t>(sa) * kAStageBytes, &tm_a, &s.a_full[sa],
-                        a.a_plane[as] * a.cin_p + kb * kBlockK, m0 - 1);
-            if (++sa == a.a_stages) {
-              sa = 0;
-              pa ^= 1;
-            }
-            if (!a.resident) {
-              for (int wi = 0; wi < a.n_w[as]; ++wi)
-                for (int tap = 0; tap < 3; ++tap) {
-                  mbar_wait(&s.b_empty[sb], pb ^ 1);
-                  mbar_arrive_expect_tx(&s.b_full[sb], b_bytes);
-                  tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb],
-                              kb * kBlockK, (a.w_plane[as][wi] * 3 + tap) * a.cout_p + n0);
-                  if (++sb == a.b_stages) {
-                    sb = 0;
-                    pb ^= 1;
-                  }
+          mbar_wait(&s.a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&s.a_full[sa], a_tx);
+          unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroupBytes;
+#pragma unroll
+          for (int ms = 0; ms < MS; ++ms)
+#pragma unroll
+            for (int ap = 0; ap < PLANES; ++ap)
+              tma_load_2d(dst + (ms * PLANES + ap) * kATileBytes, &tm_a, &s.a_full[sa],
+                          ap * a.cin_p + kb * kBlockK, m0 + ms * kBlockM);
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+          if (!RESIDENT) {
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+              for (int wp = 0; wp < WPLANES; ++wp) {
+                mbar_wait(&s.b_empty[sb], pb ^ 1);
+                mbar_arrive_expect_tx(&s.b_full[sb], b_bytes);
+                tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * kBlockK,
+                            (wp * 3 + tap) * a.cout_p + n0);
+                if (++sb == a.b_stages) {
+                  sb = 0;
+                  pb ^= 1;
                 }
-            }
+              }
           }
         }
       }
@@ -503,111 +370,138 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      if (a.resident) {
+      if (RESIDENT) {
         mbar_wait(&s.w_full, 0);
         tc_fence_after();
       }
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+      int sa = 0, sb = 0, stage = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
+      const int nk_last = (a.cin_p - (a.k_blocks - 1) * kBlockK) / 16;
+      const uint32_t acc_stride = MS * a.acc_cols;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(&s.tmem_empty[stage], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kMaxNTile;
-        uint32_t accumulate = 0;
+        const uint32_t d_base = tmem_base + stage * acc_stride;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
-          const int nk = min(kBlockK / 16, (a.cin_p - kb * kBlockK) / 16);
-          for (int as = 0; as < a.n_asteps; ++as) {
-            mbar_wait(&s.a_full[sa], pa);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_ring + static_cast<size_t>(sa) * kAStageBytes);
-            for (int wi = 0; wi < a.n_w[as]; ++wi) {
-              for (int tap = 0; tap < 3; ++tap) {
-                uint32_t b_addr;
-                if (a.resident) {
-                  b_addr = smem_u32(b_region +
-                                    static_cast<size_t>((a.w_plane[as][wi] * 3 + tap) * a.k_blocks + kb) * b_bytes);
-                } else {
-                  mbar_wait(&s.b_full[sb], pb);
-                  tc_fence_after();
-                  b_addr = smem_u32(b_region + static_cast<size_t>(sb) * b_bytes);
+          const int nk = (kb == a.k_blocks - 1) ? nk_last : (kBlockK / 16);
+          mbar_wait(&s.a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_addr = a_ring_addr + sa * kAGroupBytes;
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll
+            for (int wp = 0; wp < WPLANES; ++wp) {
+              uint32_t b_addr;
+              if (RESIDENT) {
+                b_addr = b_region_addr + ((wp * 3 + tap) * a.k_blocks + kb) * b_bytes;
+              } else {
+                mbar_wait(&s.b_full[sb], pb);
+                tc_fence_after();
+                b_addr = b_region_addr + sb * b_bytes;
+              }
+              const uint64_t db = sw128_desc(b_addr);
+#pragma unroll
+              for (int ms = 0; ms < MS; ++ms) {
+#pragma unroll
+                for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {   // W_lo only meets the hi plane
+                  const uint64_t da = sw128_desc(a_addr + (ms * PLANES + ap) * kATileBytes + tap * 128);
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    if (k < nk)
+                      umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
+                               (kb | tap | wp | ap | k) != 0);
                 }
-                const uint64_t da = umma_desc_sw128_off(a_addr + tap * 128, a.base_off_mode ? tap : 0);
-                const uint64_t db = umma_desc_sw128(b_addr);
-                for (int k = 0; k < nk; ++k) {
-                  umma_f16(d_tmem, da + 2 * k, db + 2 * k, a.idesc, accumulate);
-                  accumulate = 1;
-                }
-                if (!a.resident) {
-                  umma_commit(&s.b_empty[sb]);
-                  if (++sb == a.b_stages) {
-                    sb = 0;
-                    pb ^= 1;
-                  }
+              }
+              if (!RESIDENT) {
+                umma_commit(&s.b_empty[sb]);
+                if (++sb == a.b_stages) {
+                  sb = 0;
+                  pb ^= 1;
                 }
               }
             }
-            umma_commit(&s.a_empty[sa]);
-            if (++sa == a.a_stages) {
-              sa = 0;
-              pa ^= 1;
-            }
+          }
+          umma_commit(&s.a_empty[sa]);
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
           }
         }
-        umma_commit(&s.tmem_full[acc]);
+        umma_commit(&s.tmem_full[stage]);
+        if (++stage == a.acc_stages) {
+          stage = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
+    // ===================== epilogue: warps 2..9 = two sets x four lane quadrants =====================
     const int q = warp & 3;
-    const int et = threadIdx.x - 64;
+    const int eset = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;        // 0..255
     const bool odd = lane & 1;
     const int row_elems = a.cout_p * a.out_planes;
     const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / a.n_tiles) * kBlockM;
-      const int n0 = (tile % a.n_tiles) * a.n_tile;
-      for (int i = et; i < a.n_tile; i += 128) s.bias[acc][i] = a.bias[n0 + i];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-
-      const int r_even = (m0 + 32 * q + lane) & ~1;
-      bool valid = false, writable = false;
-      int64_t out_row = 0;
-      if (r_even < a.rows_in) {
-        const int b = r_even / a.Lp_in;
-        const int tp = (r_even - b * a.Lp_in) >> 1;
-        valid = tp < (a.len0[b] >> a.shift);
-        writable = tp < a.Lp_out;
-        out_row = static_cast<int64_t>(b) * a.Lp_out + tp;
+    const int n_chunks = a.n_tile >> 4;
+    const bool single_n = (a.n_tiles == 1);
+    if (single_n) {
+      for (int i = et; i < a.n_tile; i += kEpiThreads) s.bias[0][i] = a.bias[i];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    int stage = 0, it = 0;
+    uint32_t acc_phase = 0;
+    ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next(), ++it) {
+      const int m0 = cur.super * (MS * kBlockM);
+      const int n0 = cur.n * a.n_tile;
+      const float* bias_s = s.bias[0];
+      if (!single_n) {
+        bias_s = s.bias[it & 1];
+        for (int i = et; i < a.n_tile; i += kEpiThreads) s.bias[it & 1][i] = a.bias[n0 + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      void* orow = a.out_fp32
-                       ? static_cast<void*>(static_cast<float*>(a.out) + out_row * row_elems + n0)
-                       : static_cast<void*>(static_cast<__half*>(a.out) + out_row * row_elems + n0);
-
-      mbar_wait(&s.tmem_full[acc], acc_phase);
+      // row bookkeeping for every sub-tile (before the accumulator wait, to overlap the loads)
+      bool valid[MS], writable[MS];
+      int64_t out_row[MS];
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        valid[ms] = writable[ms] = false;
+        out_row[ms] = 0;
+        const int r_even = (m0 + ms * kBlockM + 32 * q + lane) & ~1;
+        if (r_even < a.rows_in) {
+          const uint32_t pidx = static_cast<uint32_t>(r_even) >> 1;
+          const int b = static_cast<int>((static_cast<unsigned long long>(pidx) * a.pair_magic) >> 40);
+          const int tp = static_cast<int>(pidx) - b * a.half_lp;
+          valid[ms] = tp < (__ldg(a.len0 + b) >> a.shift);
+          writable[ms] = tp < a.Lp_out;
+          out_row[ms] = static_cast<int64_t>(b) * a.Lp_out + tp;
+        }
+      }
+      mbar_wait(&s.tmem_full[stage], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * kMaxNTile;
-      int col = 0;
-      for (; col + 32 <= a.n_tile; col += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + col, v);
-        tmem_ld_wait();
-        epilogue_chunk<32>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, lo_off, a.w_inv_scale);
-      }
-      if (col < a.n_tile) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_addr + col, v);
-        tmem_ld_wait();
-        epilogue_chunk<16>(v, s.bias[acc], col, odd, valid, writable, orow, a.out_fp32, lo_off, a.w_inv_scale);
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        void* orow = a.out_fp32
+                         ? static_cast<void*>(static_cast<float*>(a.out) + out_row[ms] * row_elems + n0)
+                         : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
+                                (stage * MS + ms) * a.acc_cols;
+        for (int c = eset; c < n_chunks; c += 2) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_addr + c * 16, v);
+          tmem_ld_wait();
+          epilogue_chunk16(v, bias_s, c * 16, odd, valid[ms], writable[ms], orow, a.out_fp32, lo_off,
+                           a.w_inv_scale);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
+      if (lane == 0) mbar_arrive(&s.tmem_empty[stage]);
+      if (++stage == a.acc_stages) {
+        stage = 0;
+        acc_phase ^= 1;
+      }
     }
   }
 
@@ -617,6 +511,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvArgs);
+
+template <int MS, bool RESIDENT>
+ConvKernelFn pick_conv_planes(int planes, int wplanes) {
+  if (planes == 1 && wplanes == 1) return conv_tc_kernel<MS, 1, 1, RESIDENT>;
+  if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, RESIDENT>;
+  return conv_tc_kernel<MS, 2, 2, RESIDENT>;
+}
+ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident) {
+  if (resident) {
+    if (ms == 4) return pick_conv_planes<4, true>(planes, wplanes);
+    if (ms == 2) return pick_conv_planes<2, true>(planes, wplanes);
+    return pick_conv_planes<1, true>(planes, wplanes);
+  }
+  if (ms == 2) return pick_conv_planes<2, false>(planes, wplanes);
+  return pick_conv_planes<1, false>(planes, wplanes);
 }
 
 // ------------------------------------------------------------------------------------
@@ -877,10 +789,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
   p->B = B;
   p->max_len = max_len;
   p->ws = static_cast<char*>(workspace);
-  // RISER_CONV_IMPL: 0 = v1 (one A load per tap), 1 = v2 shifted descriptors (base_offset 0),
-  // 2 = v2 with base_offset = tap.  Development switch; the default is the validated one.
-  p->impl = env_int("RISER_CONV_IMPL", kDefaultConvImpl);
   const bool allow_resident = env_int("RISER_CONV_RESIDENT", 1) != 0;
+  const int max_ms = std::max(1, std::min(2, env_int("RISER_CONV_MS", 2)));
   plan_lengths(m, max_len, p->Lmax, p->Lp);
   const size_t need = plan_offsets(m, B, p->Lp, p->act_off);
   if (workspace_bytes < need) {
@@ -888,17 +798,48 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     return fail(RISER_ENOMEM, "riser_plan_create: workspace %zu < %zu bytes", workspace_bytes, need);
   }
   RISER_REQUIRE(static_cast<int64_t>(B) * p->Lp[1] * 8 < (int64_t(1) << 31), "riser_plan_create: B * L too large");
-  RISER_REQUIRE(p->impl != 0 || m->act_planes == 1, "riser_plan_create: the v1 kernel has no X3 mode");
   RISER_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, as_stream(stream)));
   int max_smem = 0;
   RISER_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+
+  // Early layers run read-chunk by read-chunk so that their activations stay in the L2:
+  // layer i is "chunked" while streaming its input + output through HBM would take longer
+  // than its tensor work (both per read).  From the first compute-bound layer on, layers run
+  // over the whole batch (more tiles per launch, weights amortised).
+  {
+    const double hbm_bw = 6.4e12, tensor_peak = 1.4e15;
+    const int n_terms = (m->act_planes == 2) ? 3 : m->passes;
+    int n_chunked = 1;   // layer 0 goes with layer 1
+    size_t pair_bytes = 0;
+    for (int i = 1; i < m->n_layers; ++i) {
+      const bool last = (i == m->n_layers - 1);
+      const double in_b = static_cast<double>(p->Lp[i]) * m->layer[i - 1].cout_p * m->act_planes * 2;
+      const double out_b = static_cast<double>(p->Lp[i + 1]) * m->layer[i].cout_p * (last ? 4 : m->act_planes * 2);
+      const double flops = 2.0 * 3 * m->layer[i].cin_p * m->layer[i].cout_p * p->Lp[i] * n_terms;
+      if ((in_b + out_b) / hbm_bw > 0.7 * flops / tensor_peak && n_chunked == i) {
+        n_chunked = i + 1;
+        pair_bytes = std::max(pair_bytes, static_cast<size_t>(in_b + out_b));
+      }
+    }
+    if (n_chunked == 1) n_chunked = 0;
+    const size_t l2_budget = static_cast<size_t>(env_int("RISER_L2_BUDGET_MB", 72)) << 20;
+    int chunk = pair_bytes ? static_cast<int>(std::max<size_t>(8, l2_budget / pair_bytes)) : B;
+    // Measured on B200 (profiles/README.md): with the current kernels the extra launches and
+    // wave tails of chunking cost more than the L2 hits give back, so it is opt-in.
+    if (!env_int("RISER_CHUNKING", 0)) chunk = B;
+    p->chunk_reads = std::max(1, std::min(B, env_int("RISER_CHUNK_READS", chunk)));
+    if (p->chunk_reads >= B) n_chunked = 0;
+    p->n_chunked = std::max(0, std::min(m->n_layers, env_int("RISER_CHUNKED_LAYERS", n_chunked)));
+  }
+
   for (int i = 1; i < m->n_layers; ++i) {
     const LayerPack& L = m->layer[i];
     LayerPlan& lp = p->layer[i];
     const int rows_in = B * p->Lp[i];
     const bool last = (i == m->n_layers - 1);
+    const int a_box_rows = env_int("RISER_A_BOX_ROWS", 136);   // 130 needed; a multiple of 8 is what TMA likes
     int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
-                       p->impl == 0 ? kBlockM : kARows);
+                       a_box_rows);
     if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile);
     if (st) {
       delete p;
@@ -907,7 +848,6 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     ConvArgs& a = lp.args;
     std::memset(&a, 0, sizeof(a));
     a.bias = L.bias;
-    a.len0 = nullptr;
     a.out = p->ws + p->act_off[i + 1];
     a.rows_in = rows_in;
     a.Lp_in = p->Lp[i];
@@ -917,57 +857,61 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.cout_p = L.cout_p;
     a.n_tile = L.n_tile;
     a.n_tiles = L.n_tiles;
-    a.m_tiles = (rows_in + kBlockM - 1) / kBlockM;
     a.k_blocks = (L.cin_p + kBlockK - 1) / kBlockK;
-    a.passes = m->passes;
+    a.planes = m->act_planes;
+    a.wplanes = m->passes;
     a.out_fp32 = last ? 1 : 0;
     a.out_planes = last ? 1 : m->act_planes;
     a.idesc = umma_idesc_f16(kBlockM, L.n_tile);
     a.w_inv_scale = L.w_inv_scale;
+    a.acc_cols = round_up(L.n_tile, 32);
+    a.half_lp = p->Lp[i] / 2;
+    a.a_tx_bytes = a_box_rows * 128;
+    a.pair_magic = ((1ull << 40) / static_cast<unsigned long long>(a.half_lp)) + 1ull;
     const size_t b_bytes = static_cast<size_t>(L.n_tile) * kBlockK * 2;
-    if (p->impl == 0) {
-      const size_t stage_bytes = static_cast<size_t>(kBlockM) * kBlockK * 2 + b_bytes;
-      const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
-      int stages = static_cast<int>((static_cast<size_t>(max_smem) - fixed) / stage_bytes);
-      a.stages = std::max(2, std::min(kMaxStages, stages));
-      lp.smem = fixed + a.stages * stage_bytes;
+    const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
+    const size_t avail = static_cast<size_t>(max_smem) - fixed;
+    const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
+    const size_t a_group1 = static_cast<size_t>(m->act_planes) * kATileBytes;
+    if (allow_resident && L.n_tiles == 1 && w_all + 2 * a_group1 <= avail) {
+      // resident weights; as many 128-row sub-tiles per work item as leave >= 2 accumulator
+      // stages and >= 2 A groups in flight (amortises the per-item bookkeeping of small-N layers)
+      a.resident = 1;
+      a.ms = 1;
+      const int want_ms = std::max(1, std::min(4, env_int("RISER_CONV_MS_RES", 4)));
+      for (int ms = want_ms; ms > 1; ms >>= 1)
+        if (2 * ms * a.acc_cols <= kTmemCols && w_all + 2 * ms * a_group1 <= avail &&
+            static_cast<int64_t>(rows_in) / (ms * kBlockM) >= 2 * m->sm_count) {
+          a.ms = ms;
+          break;
+        }
+      a.b_stages = 1;
+      a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / (a.ms * a_group1)));
+      lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * a.ms * a_group1;
     } else {
-      a.base_off_mode = (p->impl == 2) ? 1 : 0;
-      a.n_wplanes = m->passes;
-      // A steps: hi plane x {W_hi [, W_lo]}, then (X3) lo plane x {W_hi}
-      a.n_asteps = m->act_planes;
-      a.a_plane[0] = 0;
-      a.n_w[0] = m->passes;
-      a.w_plane[0][0] = 0;
-      a.w_plane[0][1] = 1;
-      a.a_plane[1] = 1;
-      a.n_w[1] = 1;
-      a.w_plane[1][0] = 0;
-      const size_t fixed = 1024 + sizeof(ConvSmem2) + 64;
-      const size_t avail = static_cast<size_t>(max_smem) - fixed;
-      const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
-      const int min_a = 3;
-      if (allow_resident && L.n_tiles == 1 && w_all + static_cast<size_t>(min_a) * kAStageBytes <= avail) {
-        a.resident = 1;
-        a.b_stages = 1;
-        a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / kAStageBytes));
-        lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * kAStageBytes;
-      } else {
-        a.resident = 0;
-        // split the budget: A ring gets ~1/3 (at least 2 stages), B ring the rest
-        int a_st = std::max(2, std::min<int>(4, static_cast<int>(avail / 3 / kAStageBytes)));
-        int b_st = static_cast<int>((avail - static_cast<size_t>(a_st) * kAStageBytes) / b_bytes);
-        b_st = std::max(2, std::min(kMaxBStages, b_st));
-        a_st = std::min<int>(kMaxAStages, static_cast<int>((avail - static_cast<size_t>(b_st) * b_bytes) / kAStageBytes));
-        a.a_stages = a_st;
-        a.b_stages = b_st;
-        lp.smem = fixed + static_cast<size_t>(a_st) * kAStageBytes + static_cast<size_t>(b_st) * b_bytes;
+      a.resident = 0;
+      a.ms = (2 * a.acc_cols <= kTmemCols) ? max_ms : 1;
+      // smem split: at least 2 A groups and 2 B stages; prefer 3+ B stages
+      while (a.ms > 1 && 2 * a.ms * a_group1 + 2 * b_bytes > avail) --a.ms;
+      const size_t a_group = a.ms * a_group1;
+      int a_st = 2;
+      int b_st = static_cast<int>((avail - a_st * a_group) / b_bytes);
+      if (b_st > 4 && (a_st + 1) * a_group + 4 * b_bytes <= avail) {
+        a_st = 3;
+        b_st = static_cast<int>((avail - a_st * a_group) / b_bytes);
       }
+      a.a_stages = a_st;
+      a.b_stages = std::max(2, std::min(kMaxBStages, b_st));
+      lp.smem = fixed + static_cast<size_t>(a.a_stages) * a_group + static_cast<size_t>(a.b_stages) * b_bytes;
     }
-    lp.grid = std::min(a.m_tiles * a.n_tiles, m->sm_count);
+    a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+    lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
   }
-  RISER_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  RISER_CUDA_TRY(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  for (int ms = 1; ms <= 4; ms <<= 1)
+    for (int pl = 0; pl < 3; ++pl)
+      for (int res = (ms == 4 ? 1 : 0); res < 2; ++res)
+        RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, res)),
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   *out = p;
   return RISER_OK;
 }
@@ -977,7 +921,12 @@ extern "C" int riser_plan_destroy(riser_plan* p) {
   return RISER_OK;
 }
 
-extern "C" int riser_forward_launches(const riser_plan* p) { return p ? p->model->n_layers + 1 : 0; }
+extern "C" int riser_forward_launches(const riser_plan* p) {
+  if (!p) return 0;
+  const int n = p->model->n_layers;
+  const int chunks = p->n_chunked > 0 ? (p->B + p->chunk_reads - 1) / p->chunk_reads : 0;
+  return chunks * p->n_chunked + (n - p->n_chunked) + 1 + (p->n_chunked == 0 ? 0 : 0);
+}
 
 extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
                                      int* channels_padded, int* channels, int* n_tile) {
@@ -992,33 +941,63 @@ extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset
   return RISER_OK;
 }
 
+namespace riser {
+namespace {
+
+int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len, int b0, int nb,
+                  cudaStream_t st) {
+  const riser_model* m = p->model;
+  const LayerPack& L = m->layer[0];
+  const int64_t total = static_cast<int64_t>(nb) * p->Lp[1] * (L.cout_p / 8);
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 32));
+  __half* out = reinterpret_cast<__half*>(p->ws + p->act_off[1]) +
+                static_cast<int64_t>(b0) * p->Lp[1] * L.cout_p * m->act_planes;
+  layer0_kernel<<<grid, 256, 0, st>>>(x + static_cast<int64_t>(b0) * ld_x, ld_x, len + b0, L.w0, L.bias, out, nb,
+                                      p->Lp[1], L.cout, L.cout_p, m->act_planes);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+// conv layer i over reads [b0, b0 + nb): the super-tiles that touch those reads' rows
+int launch_conv(const riser_plan* p, int i, const int32_t* len, int b0, int nb, cudaStream_t st) {
+  const LayerPlan& lp = p->layer[i];
+  ConvArgs a = lp.args;
+  a.len0 = len;
+  const int64_t rows_per_super = static_cast<int64_t>(a.ms) * kBlockM;
+  const int64_t row0 = static_cast<int64_t>(b0) * a.Lp_in, row1 = static_cast<int64_t>(b0 + nb) * a.Lp_in;
+  a.super0 = static_cast<int>(row0 / rows_per_super);
+  a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
+  const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident)<<<grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+}  // namespace
+}  // namespace riser
+
+// stage 0: the chunked early layers (layer 0 + conv layers < n_chunked), chunk by chunk;
+// stage 1: the remaining conv layers over the whole batch; stage 2: head.
 extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
                                    const int32_t* len, float* probs, float* feat, riser_stream_t stream) {
   RISER_REQUIRE(p && len, "riser_forward_stage: null pointer");
   const riser_model* m = p->model;
   cudaStream_t st = as_stream(stream);
+  int rc = RISER_OK;
   if (stage == 0) {
     RISER_REQUIRE(x, "riser_forward_stage: null x");
     RISER_REQUIRE(ld_x >= p->max_len && (ld_x & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
                   "riser_forward: x must be 8-byte aligned with even ld_x >= max_len");
-    const LayerPack& L = m->layer[0];
-    const int64_t total = static_cast<int64_t>(p->B) * p->Lp[1] * (L.cout_p / 8);
-    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 32));
-    layer0_kernel<<<grid, 256, 0, st>>>(x, ld_x, len, L.w0, L.bias,
-                                        reinterpret_cast<__half*>(p->ws + p->act_off[1]), p->B, p->Lp[1],
-                                        L.cout, L.cout_p, m->act_planes);
-    RISER_CUDA_TRY(cudaGetLastError());
-  } else if (stage == 1) {
-    for (int i = 1; i < m->n_layers; ++i) {
-      const LayerPlan& lp = p->layer[i];
-      ConvArgs a = lp.args;
-      a.len0 = len;
-      if (p->impl == 0)
-        conv_tc_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
-      else
-        conv_tc2_kernel<<<lp.grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
-      RISER_CUDA_TRY(cudaGetLastError());
+    if (p->n_chunked == 0) return launch_layer0(p, x, ld_x, len, 0, p->B, st);
+    for (int b0 = 0; b0 < p->B; b0 += p->chunk_reads) {
+      const int nb = std::min(p->chunk_reads, p->B - b0);
+      if ((rc = launch_layer0(p, x, ld_x, len, b0, nb, st))) return rc;
+      for (int i = 1; i < p->n_chunked; ++i)
+        if ((rc = launch_conv(p, i, len, b0, nb, st))) return rc;
     }
+  } else if (stage == 1) {
+    for (int i = std::max(1, p->n_chunked); i < m->n_layers; ++i)
+      if ((rc = launch_conv(p, i, len, 0, p->B, st))) return rc;
   } else if (stage == 2) {
     RISER_REQUIRE(probs, "riser_forward_stage: null probs");
     const int n = m->n_layers;
@@ -1026,8 +1005,13 @@ extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* 
                                                m->fc_b, probs, feat, p->B, p->Lp[n], m->layer[n - 1].cout_p,
                                                m->c_last, n);
     RISER_CUDA_TRY(cudaGetLastError());
+  } else if (stage == 3) {   // layer-0 launches only (timing aid: see bench.py)
+    RISER_REQUIRE(x, "riser_forward_stage: null x");
+    if (p->n_chunked == 0) return launch_layer0(p, x, ld_x, len, 0, p->B, st);
+    for (int b0 = 0; b0 < p->B; b0 += p->chunk_reads)
+      if ((rc = launch_layer0(p, x, ld_x, len, b0, std::min(p->chunk_reads, p->B - b0), st))) return rc;
   } else {
-    return fail(RISER_EINVAL, "riser_forward_stage: stage %d outside 0..2", stage);
+    return fail(RISER_EINVAL, "riser_forward_stage: stage %d outside 0..3", stage);
   }
   return RISER_OK;
 }

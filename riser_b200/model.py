@@ -19,7 +19,7 @@ PREC_F16_W2 = 1    # two passes, weights split hi + lo (exact to ~22 bits)
 PREC_F16_X3 = 2    # three passes, weights and activations split hi + lo: fp32-class
 DEFAULT_PRECISION = PREC_F16_X3
 MIN_LENGTH = 4096  # riser/preprocess.py:8 -- 12 stride-2 pools
-DEFAULT_CHUNK = 256  # reads per network sub-batch (activations of one sub-batch fit the L2)
+DEFAULT_CHUNK = 0    # 0 = whole batch in one plan (the plan chunks the early layers itself)
 
 
 class Plan:
@@ -165,16 +165,17 @@ class Model():
         ld), lens: int32 [B] valid lengths (>= 4096; shorter -> NaN row).
         Returns probs fp32 [B, 2] on the device.  No synchronisation.
 
-        chunk: run the network over sub-batches of this many reads so that the
-        inter-layer activations of one sub-batch stay resident in the 126 MB L2
-        (default: DEFAULT_CHUNK when B is larger).
-        events: optional list; (start, end) torch.cuda.Event pairs bracketing the
-        tcgen05 conv stage of every sub-batch are appended (bench.py's roofline)."""
+        chunk: optionally run the network over sub-batches of this many reads (the
+        library already runs the memory-bound early layers chunk by chunk inside one
+        plan so their activations stay in the 126 MB L2; this only bounds workspace).
+        events: optional list; (start, end) torch.cuda.Event pairs bracketing layer 0 +
+        the tcgen05 conv layers of every sub-batch are appended (bench.py's roofline;
+        ``time_layer0`` gives the layer-0 share to subtract)."""
         B = x.shape[0]
         max_len = int(max_len if max_len is not None else x.shape[1])
         if probs is None:
             probs = torch.empty(B, 2, dtype=torch.float32, device=self.device)
-        chunk = int(chunk or DEFAULT_CHUNK)
+        chunk = int(chunk or DEFAULT_CHUNK or B)
         L = _lib.lib()
         stream = _lib.stream_ptr()
         for lo in range(0, B, chunk):
@@ -186,10 +187,10 @@ class Model():
                 _lib.check(L.riser_forward(p._handle, _lib.ptr(xs), x.stride(0), _lib.ptr(ls), _lib.ptr(ps),
                                            _lib.ptr(fs), stream), "riser_forward")
                 continue
+            # stages 0 (layer 0 + chunked early conv layers) and 1 (remaining conv layers) bracketed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             for stage in range(3):
-                if stage == 1:
-                    e0.record()
                 _lib.check(L.riser_forward_stage(p._handle, stage, _lib.ptr(xs), x.stride(0), _lib.ptr(ls),
                                                  _lib.ptr(ps), _lib.ptr(fs), stream), "riser_forward_stage")
                 if stage == 1:
@@ -197,9 +198,23 @@ class Model():
             events.append((e0, e1))
         return probs
 
+    def time_layer0(self, x, lens, max_len, iters=3):
+        """Device time (ms) of the layer-0 launches alone (same chunk loop as a forward)."""
+        p = self.plan(x.shape[0], max_len)
+        L, stream = _lib.lib(), _lib.stream_ptr()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for k in range(iters + 1):
+            if k == 1:
+                e0.record()
+            _lib.check(L.riser_forward_stage(p._handle, 3, _lib.ptr(x), x.stride(0), _lib.ptr(lens), None, None,
+                                             stream), "riser_forward_stage")
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+
     def launches(self, B, max_len, chunk=None):
         """Kernels one classify_batch call launches."""
-        chunk = int(chunk or DEFAULT_CHUNK)
+        chunk = int(chunk or DEFAULT_CHUNK or B)
         return sum(self.plan(min(chunk, B - lo), max_len).launches for lo in range(0, B, chunk))
 
 

@@ -31,7 +31,7 @@ class BatchedClassifier:
         self.models = list(models)
         self.proc = processor
         self.device = _lib.require_device()
-        self.chunk = int(chunk or DEFAULT_CHUNK)
+        self.chunk = int(chunk or DEFAULT_CHUNK or 0)
         self.min_len = processor.get_min_length()
         self.max_len = processor.get_max_length()
         self.fixed_trim = processor.get_fixed_trim_length()

@@ -48,4 +48,4 @@ for name, fn in (("normalise", lambda: proc.mad_normalise_batch(batch, out=x)),
         if flops:
             extra = f"  {flops * B / ms / 1e9:.1f} TFLOP/s algorithmic"
     print(f"{name}: {ms:.3f} ms / batch of {B} x {L}  -> {B / ms * 1e3:.0f} reads/s{extra}")
-print("p_on[:4]", probs[:4, 1].tolist())
+print("p_on[:4]", probs[:4, 1].tolist(), "layer0 ms", model.time_layer0(x, lens, L))
