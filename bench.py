@@ -294,7 +294,8 @@ def main():
         tensor_peak, hbm_peak, peak_src = peaks()
         reads = B * world * args.steps
         value = reads / (total_ms * 1e-3)
-        conv_flops = conv_stack_flops_per_read(L) * B
+        fused = mdl.plan(B, L).fused_layer0       # layer 0 then runs inside the conv kernel
+        conv_flops = (conv_stack_flops_per_read(L) + (2 * 3 * CHANNELS[0] * L if fused else 0)) * B
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_stack_traffic.json")
@@ -312,7 +313,7 @@ def main():
             "config": {"workload": workload_name(B, L), "precision_mode": precision, "chunk": clf.chunk,
                        "cache": "L2 flushed between steps (256 MiB write); inputs 393 MB > L2",
                        "flops_per_read": flops_per_read(L), "decisions_made": n_dec},
-            "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (layers 1-11, 11 launches per sub-batch)",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "share_of_step": conv_ms / (total_ms / args.steps)},

@@ -161,6 +161,10 @@ int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t 
 /* Number of kernels one riser_forward launches (for gpu_launches accounting). */
 int riser_forward_launches(const riser_plan* p);
 
+/* 1 when the plan computes layer 0 inside layer 1's kernel (its activation buffer is then
+ * never written and stage 3 launches nothing). */
+int riser_plan_fused_layer0(const riser_plan* p);
+
 /* Introspection for tests / profiling: layer i (1..n_layers) reads (i < n) or, for
  * i == n_layers, the head reads, an activation buffer at workspace + *offset laid out
  * [B * *rows_per_read][*channels_padded], fp16 for i < n_layers, fp32 for i == n_layers.

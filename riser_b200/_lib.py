@@ -32,6 +32,7 @@ SIGNATURES = {
     "riser_forward": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "riser_forward_stage": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "riser_forward_launches": (c_int, [c_void_p]),
+    "riser_plan_fused_layer0": (c_int, [c_void_p]),
     "riser_plan_layer_info": (c_int, [c_void_p, c_int, P(c_i64), P(c_int), P(c_int), P(c_int), P(c_int)]),
     "riser_decide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
 }

@@ -96,6 +96,12 @@ struct ConvArgs {
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x 128)
+  // fused layer 0 (layer 1 only): A tiles are computed in-kernel from the normalised signal
+  const float* x;
+  long long ld_x;
+  const float* w0;        // layer-0 weights [cout0][3], bias [cout0]
+  const float* b0;
+  int cout0;
   unsigned long long pair_magic;   // floor(2^40 / half_lp) + 1: pair index -> read index
   uint32_t idesc;
   float w_inv_scale;
@@ -114,6 +120,7 @@ struct LayerPlan {
 struct riser_plan {
   const riser_model* model = nullptr;
   int B = 0, max_len = 0;
+  int fuse_l0 = 0;                      // layer 0 computed inside layer 1's kernel
   int chunk_reads = 0, n_chunked = 0;   // early layers 0..n_chunked-1 run chunk by chunk (L2 residency)
   int Lmax[riser::kMaxLayers + 1];
   int Lp[riser::kMaxLayers + 1];
@@ -193,6 +200,7 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
 constexpr int kATileBytes = 136 * 128;      // smem stride of one A tile, multiple of 1024
 constexpr int kMaxAStages = 8, kMaxBStages = 8, kMaxAccStages = 4;
 constexpr int kConvThreads = 320;
+constexpr int kCvtThreads = 288;         // fused layer 0: converter warps 10..18 (514 rows = 2 passes)
 constexpr int kEpiThreads = 256;
 
 struct ConvSmem {
@@ -202,6 +210,7 @@ struct ConvSmem {
   uint64_t tmem_full[kMaxAccStages], tmem_empty[kMaxAccStages];
   uint32_t tmem_base;
   float bias[2][kMaxNTile];
+  float4 w0q[32];        // fused layer 0: {w[c][0], w[c][1], w[c][2], bias[c]} per output channel
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -270,15 +279,17 @@ struct ItemCursor {
   }
 };
 
-template <int MS, int PLANES, int WPLANES, bool RESIDENT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false>
+__global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
   constexpr int kATiles = MS * PLANES;                       // A tiles per K block
-  constexpr uint32_t kAGroupBytes = kATiles * kATileBytes;
+  // fused layer 0: one contiguous (MS*128 + 2)-row tile per plane instead of MS haloed tiles
+  constexpr uint32_t kFusedTileBytes = (MS * kBlockM + 8) * 128;
+  constexpr uint32_t kAGroupBytes = FUSED ? PLANES * kFusedTileBytes : kATiles * kATileBytes;
   const uint32_t b_bytes = a.n_tile * kBlockK * 2;
   unsigned char* a_ring = base;
   unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroupBytes;
@@ -294,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int i = 0; i < a.a_stages; ++i) {
-      mbar_init(&s.a_full[i], 1);
+      mbar_init(&s.a_full[i], FUSED ? kCvtThreads : 1);
       mbar_init(&s.a_empty[i], 1);
     }
     for (int i = 0; i < a.b_stages; ++i) {
@@ -332,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t pa = 0, pb = 0;
       const uint32_t a_tx = kATiles * a.a_tx_bytes;
       ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+      for (int item = blockIdx.x; !FUSED && item < n_items; item += gridDim.x, cur.next()) {
         const int m0 = cur.super * (MS * kBlockM) - 1;
         const int n0 = cur.n * a.n_tile;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
@@ -405,7 +416,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               for (int ms = 0; ms < MS; ++ms) {
 #pragma unroll
                 for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {   // W_lo only meets the hi plane
-                  const uint64_t da = sw128_desc(a_addr + (ms * PLANES + ap) * kATileBytes + tap * 128);
+                  const uint64_t da = FUSED ? sw128_desc(a_addr + ap * kFusedTileBytes + (ms * kBlockM + tap) * 128)
+                                            : sw128_desc(a_addr + (ms * PLANES + ap) * kATileBytes + tap * 128);
 #pragma unroll
                   for (int k = 0; k < kBlockK / 16; ++k)
                     if (k < nk)
@@ -435,7 +447,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     }
-  } else {
+  } else if (FUSED && warp >= 10) {
+    // ===================== fused layer 0: converter warps 10..17 =====================
+    // Compute layer 1's A operand (layer 0 = Conv1d(1->C0,k3,same)+ReLU+MaxPool(2,2), fp32 on
+    // CUDA cores, nets/cnn.py:55-64) straight into shared memory in the SWIZZLE_128B K-major
+    // layout the MMA reads: row j of the tile at byte j*128, 16-byte chunk c at (c ^ (j & 7)).
+    const int ct = threadIdx.x - kConvThreads;
+    for (int c = ct; c < 32; c += kCvtThreads)
+      s.w0q[c] = (c < a.cout0) ? make_float4(a.w0[c * 3], a.w0[c * 3 + 1], a.w0[c * 3 + 2], a.b0[c])
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("bar.sync 2, %0;" ::"n"(kCvtThreads) : "memory");
+    constexpr int kRows = MS * kBlockM + 2;
+    const int live_c8 = (a.cout0 + 7) >> 3;            // 8-channel chunks that hold real channels
+    int sa = 0;
+    uint32_t pa = 0;
+    ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+      const int r0 = cur.super * (MS * kBlockM) - 1;
+      mbar_wait(&s.a_empty[sa], pa ^ 1);
+      unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroupBytes;
+      for (int j = ct; j < kRows; j += kCvtThreads) {
+        const int r = r0 + j;
+        float xm1 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        bool live = false;
+        if (r >= 0 && r < a.rows_in) {
+          const uint32_t pidx = static_cast<uint32_t>(r) >> 1;
+          const int b = static_cast<int>((static_cast<unsigned long long>(pidx) * a.pair_magic) >> 40);
+          const int tp = r - b * a.Lp_in;
+          const int L = __ldg(a.len0 + b);
+          if (tp < (L >> 1)) {
+            live = true;
+            const float* xr = a.x + static_cast<long long>(b) * a.ld_x + 2 * tp;
+            const float2 x01 = __ldg(reinterpret_cast<const float2*>(xr));
+            x0 = x01.x;
+            x1 = x01.y;
+            xm1 = (tp > 0) ? __ldg(xr - 1) : 0.f;
+            x2 = (2 * tp + 2 < L) ? __ldg(xr + 2) : 0.f;
+          }
+        }
+        unsigned char* row = dst + j * 128;
+        const int sw = j & 7;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint4 hv = make_uint4(0, 0, 0, 0), lv = make_uint4(0, 0, 0, 0);
+          if (live && c8 < live_c8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 w = s.w0q[c8 * 8 + 2 * e + h];
+                const float y0 = fmaf(w.z, x1, fmaf(w.y, x0, fmaf(w.x, xm1, w.w)));
+                const float y1 = fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w)));
+                v[h] = fminf(fmaxf(fmaxf(y0, y1), 0.f), 65504.f);
+              }
+              const __half2 hh = __floats2half2_rn(v[0], v[1]);
+              hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              if (PLANES == 2) {
+                const float2 back = __half22float2(hh);
+                const __half2 hl = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+                lo[e] = *reinterpret_cast<const uint32_t*>(&hl);
+              }
+            }
+            hv = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (PLANES == 2) lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          const int off = (c8 ^ sw) << 4;
+          *reinterpret_cast<uint4*>(row + off) = hv;
+          if (PLANES == 2) *reinterpret_cast<uint4*>(row + kFusedTileBytes + off) = lv;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
+      mbar_arrive(&s.a_full[sa]);
+      if (++sa == a.a_stages) {
+        sa = 0;
+        pa ^= 1;
+      }
+    }
+  } else if (warp < 10) {
     // ===================== epilogue: warps 2..9 = two sets x four lane quadrants =====================
     const int q = warp & 3;
     const int eset = (warp - 2) >> 2;
@@ -521,7 +611,18 @@ ConvKernelFn pick_conv_planes(int planes, int wplanes) {
   if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, RESIDENT>;
   return conv_tc_kernel<MS, 2, 2, RESIDENT>;
 }
-ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident) {
+template <int MS>
+ConvKernelFn pick_conv_fused(int planes, int wplanes) {
+  if (planes == 1 && wplanes == 1) return conv_tc_kernel<MS, 1, 1, true, true>;
+  if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, true, true>;
+  return conv_tc_kernel<MS, 2, 2, true, true>;
+}
+ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0) {
+  if (fused) {
+    if (ms == 4) return pick_conv_fused<4>(planes, wplanes);
+    if (ms == 2) return pick_conv_fused<2>(planes, wplanes);
+    return pick_conv_fused<1>(planes, wplanes);
+  }
   if (resident) {
     if (ms == 4) return pick_conv_planes<4, true>(planes, wplanes);
     if (ms == 2) return pick_conv_planes<2, true>(planes, wplanes);
@@ -888,6 +989,23 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b_stages = 1;
       a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / (a.ms * a_group1)));
       lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * a.ms * a_group1;
+      if (i == 1 && L.cin_p == 32 && env_int("RISER_FUSE_L0", 1)) {
+        // fused layer 0: A tiles are written by converter warps; one contiguous
+        // (ms*128 + 8)-row tile per plane and stage
+        for (int ms = want_ms; ms >= 1; ms >>= 1) {
+          const size_t group = static_cast<size_t>(m->act_planes) * (ms * kBlockM + 8) * 128;
+          if (2 * ms * a.acc_cols <= kTmemCols && w_all + 2 * group <= avail) {
+            p->fuse_l0 = 1;
+            a.ms = ms;
+            a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / group));
+            lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * group;
+            a.w0 = m->layer[0].w0;
+            a.b0 = m->layer[0].bias;
+            a.cout0 = m->layer[0].cout;
+            break;
+          }
+        }
+      }
     } else {
       a.resident = 0;
       a.ms = (2 * a.acc_cols <= kTmemCols) ? max_ms : 1;
@@ -908,10 +1026,13 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
   }
   for (int ms = 1; ms <= 4; ms <<= 1)
-    for (int pl = 0; pl < 3; ++pl)
+    for (int pl = 0; pl < 3; ++pl) {
       for (int res = (ms == 4 ? 1 : 0); res < 2; ++res)
         RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, res)),
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, 1, 1)),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    }
   *out = p;
   return RISER_OK;
 }
@@ -925,8 +1046,11 @@ extern "C" int riser_forward_launches(const riser_plan* p) {
   if (!p) return 0;
   const int n = p->model->n_layers;
   const int chunks = p->n_chunked > 0 ? (p->B + p->chunk_reads - 1) / p->chunk_reads : 0;
-  return chunks * p->n_chunked + (n - p->n_chunked) + 1 + (p->n_chunked == 0 ? 0 : 0);
+  const int l0 = p->fuse_l0 ? (p->n_chunked > 0 ? chunks : 1) : 0;   // layer-0 launches that fusion removes
+  return chunks * p->n_chunked + (n - p->n_chunked) + 1 - l0;
 }
+
+extern "C" int riser_plan_fused_layer0(const riser_plan* p) { return p ? p->fuse_l0 : 0; }
 
 extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
                                      int* channels_padded, int* channels, int* n_tile) {
@@ -947,6 +1071,7 @@ namespace {
 int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len, int b0, int nb,
                   cudaStream_t st) {
   const riser_model* m = p->model;
+  if (p->fuse_l0) return RISER_OK;       // computed inside layer 1's kernel
   const LayerPack& L = m->layer[0];
   const int64_t total = static_cast<int64_t>(nb) * p->Lp[1] * (L.cout_p / 8);
   const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(m->sm_count) * 32));
@@ -959,16 +1084,23 @@ int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32
 }
 
 // conv layer i over reads [b0, b0 + nb): the super-tiles that touch those reads' rows
-int launch_conv(const riser_plan* p, int i, const int32_t* len, int b0, int nb, cudaStream_t st) {
+int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const int32_t* len, int b0, int nb,
+                cudaStream_t st) {
   const LayerPlan& lp = p->layer[i];
   ConvArgs a = lp.args;
   a.len0 = len;
+  const int fused = (i == 1 && p->fuse_l0) ? 1 : 0;
+  if (fused) {
+    RISER_REQUIRE(x, "riser_forward: null x");
+    a.x = x;
+    a.ld_x = ld_x;
+  }
   const int64_t rows_per_super = static_cast<int64_t>(a.ms) * kBlockM;
   const int64_t row0 = static_cast<int64_t>(b0) * a.Lp_in, row1 = static_cast<int64_t>(b0 + nb) * a.Lp_in;
   a.super0 = static_cast<int>(row0 / rows_per_super);
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
-  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident)<<<grid, kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused)<<<grid, fused ? kConvThreads + kCvtThreads : kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
@@ -993,11 +1125,11 @@ extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* 
       const int nb = std::min(p->chunk_reads, p->B - b0);
       if ((rc = launch_layer0(p, x, ld_x, len, b0, nb, st))) return rc;
       for (int i = 1; i < p->n_chunked; ++i)
-        if ((rc = launch_conv(p, i, len, b0, nb, st))) return rc;
+        if ((rc = launch_conv(p, i, x, ld_x, len, b0, nb, st))) return rc;
     }
   } else if (stage == 1) {
     for (int i = std::max(1, p->n_chunked); i < m->n_layers; ++i)
-      if ((rc = launch_conv(p, i, len, 0, p->B, st))) return rc;
+      if ((rc = launch_conv(p, i, x, ld_x, len, 0, p->B, st))) return rc;
   } else if (stage == 2) {
     RISER_REQUIRE(probs, "riser_forward_stage: null probs");
     const int n = m->n_layers;

@@ -35,6 +35,7 @@ class Plan:
                                        _lib.ptr(self.workspace), nbytes, _lib.stream_ptr()),
                    "riser_plan_create")
         self.launches = L.riser_forward_launches(self._handle)
+        self.fused_layer0 = bool(L.riser_plan_fused_layer0(self._handle))
 
     def layer_info(self, i):
         off, rows, cp, c, nt = ctypes.c_int64(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

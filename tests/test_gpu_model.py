@@ -48,10 +48,10 @@ def oracle_layers(state, x):
     return outs
 
 
-@pytest.mark.parametrize("impl,precision", [(0, PREC_F16), (0, PREC_F16_W2), (1, PREC_F16), (1, PREC_F16_W2),
-                                            (1, PREC_F16_X3)])
-def test_every_layer_against_oracle(impl, precision, monkeypatch):
-    monkeypatch.setenv("RISER_CONV_IMPL", str(impl))
+@pytest.mark.parametrize("fuse,precision", [(0, PREC_F16), (0, PREC_F16_W2), (0, PREC_F16_X3), (1, PREC_F16),
+                                            (1, PREC_F16_W2), (1, PREC_F16_X3)])
+def test_every_layer_against_oracle(fuse, precision, monkeypatch):
+    monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
     rng = np.random.default_rng(0)
     lengths = [4096, 5001, 7108, 12048, 12047, 8615, 4097]
     normed = [pp.mad_normalise(synth.body(rng, n)) for n in lengths]
@@ -62,10 +62,11 @@ def test_every_layer_against_oracle(impl, precision, monkeypatch):
     probs = model.classify_batch(x, lens, max_len=12048, feat=feat)
     torch.cuda.synchronize()
     plan = model.plan(len(lengths), 12048)
+    assert plan.fused_layer0 == bool(fuse)
     report = []
     for b, v in enumerate(normed):
         want = oracle_layers(state, torch.from_numpy(np.asarray(v, dtype=np.float64)).float())
-        for i in range(1, 13):
+        for i in range(2 if plan.fused_layer0 else 1, 13):
             act = plan.activation(i, 12, planes=2 if precision == PREC_F16_X3 else 1)[b].float().cpu()
             w = want[i - 1].T                                  # [L_i, C]
             L = w.shape[0]
