@@ -4,8 +4,8 @@ Kit / SignalProcessor / Model / SequencerControl call surface."""
 from .preprocess import Kit, SignalProcessor, RaggedBatch      # noqa: F401
 from .model import Model, decide, PREC_F16, PREC_F16_W2, PREC_F16_X3   # noqa: F401
 
-from .pipeline import BatchedClassifier                         # noqa: F401,E402
+from .pipeline import BatchedClassifier, FixedBatchPipeline     # noqa: F401,E402
 from .control import SequencerControl                           # noqa: F401,E402
 
 __all__ = ["Kit", "SignalProcessor", "RaggedBatch", "Model", "decide", "PREC_F16", "PREC_F16_W2", "PREC_F16_X3",
-           "BatchedClassifier", "SequencerControl"]
+           "BatchedClassifier", "FixedBatchPipeline", "SequencerControl"]

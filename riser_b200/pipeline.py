@@ -134,3 +134,66 @@ class BatchedClassifier:
             if res.decisions[r] != SKIPPED and len(polyA_cache) >= 1000:
                 polyA_cache.clear()
         return res
+
+
+class FixedBatchPipeline:
+    """Double-buffered host -> device -> host pipeline for fixed-shape batches of
+    already-trimmed chunks (BASELINE config 2 / offline throughput): the H2D copy of
+    batch k+1 (copy stream) overlaps the kernels of batch k (compute stream); results
+    (decision bytes + probabilities) come back through pinned buffers.
+
+        pipe = FixedBatchPipeline(clf, B, L, threshold=0.9, mode="deplete")
+        t = pipe.submit(host_int16)          # pinned int16 [B, L]; returns immediately
+        decisions, probs = pipe.result(t)    # numpy views, valid until the slot is reused
+    """
+    def __init__(self, clf, B, L, threshold, mode, slots=2):
+        self.clf, self.B, self.L = clf, int(B), int(L)
+        self.threshold, self.mode = threshold, mode
+        dev, M = clf.device, len(clf.models)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        padded = (self.L + 7) & ~7
+        off = torch.arange(self.B + 1, dtype=torch.int64) * padded
+        self.start = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.length = torch.full((self.B,), self.L, dtype=torch.int32, device=dev)
+        self.slots = []
+        for _ in range(slots):
+            batch = RaggedBatch.__new__(RaggedBatch)
+            batch.B = self.B
+            batch.n_host = np.full(self.B, self.L, dtype=np.int32)
+            batch.sig = torch.zeros(self.B * padded + 8, dtype=torch.int16, device=dev)
+            batch.off = off.to(dev)
+            batch.n = self.length
+            batch.h2d_bytes = self.B * self.L * 2
+            self.slots.append({
+                "batch": batch, "padded": padded,
+                "copied": torch.cuda.Event(), "done": torch.cuda.Event(),
+                "dec": torch.empty(self.B, dtype=torch.uint8).pin_memory(),
+                "probs": torch.empty(M, self.B, 2, dtype=torch.float32).pin_memory(),
+                "busy": False,
+            })
+        self.n_submitted = 0
+        self.h2d_bytes = self.B * self.L * 2
+        self.d2h_bytes = self.B * (1 + 8 * M)
+
+    def submit(self, host):
+        slot = self.slots[self.n_submitted % len(self.slots)]
+        compute = torch.cuda.current_stream()
+        if slot["busy"]:
+            self.copy_stream.wait_event(slot["done"])      # the slot's previous batch has been consumed
+        with torch.cuda.stream(self.copy_stream):
+            dst = slot["batch"].sig[:self.B * slot["padded"]].view(self.B, slot["padded"])[:, :self.L]
+            dst.copy_(host, non_blocking=True)
+            slot["copied"].record(self.copy_stream)
+        compute.wait_event(slot["copied"])
+        decisions, probs = self.clf.run_windows(slot["batch"], self.start, self.length, self.threshold, self.mode)
+        slot["dec"].copy_(decisions, non_blocking=True)
+        slot["probs"].copy_(probs, non_blocking=True)
+        slot["done"].record(compute)
+        slot["busy"] = True
+        self.n_submitted += 1
+        return self.n_submitted - 1
+
+    def result(self, ticket):
+        slot = self.slots[ticket % len(self.slots)]
+        slot["done"].synchronize()
+        return slot["dec"].numpy(), slot["probs"].numpy()

@@ -91,3 +91,29 @@ def test_rna004_kit_and_empty_batch():
     res = clf.classify_batch([s for _, s in reads], [r for r, _ in reads], {}, 0.9, "deplete")
     dec_o, p_on_o, _, len_o, _ = ctl.run_batch(reads, [synth.state_dict(0)], "RNA004", {}, 0.9, "deplete")
     assert np.array_equal(res.sig_len, len_o) and np.abs(res.p_on - p_on_o).max() < 1e-3
+
+
+def test_fixed_batch_pipeline_double_buffering():
+    """The overlapped host->device->host pipeline returns, for every submitted batch, what
+    the oracle gives for THAT batch (slot reuse must not mix batches)."""
+    import torch
+    from riser_b200 import FixedBatchPipeline
+    from oracle import preprocess_oracle as pp, convnet_oracle as net
+    B, L = 6, 8615
+    proc = SignalProcessor(Kit.create_from_version("RNA004"))
+    clf = BatchedClassifier(models_for(["mRNA"]), proc)
+    pipe = FixedBatchPipeline(clf, B, L, 0.9, "deplete")
+    state = synth.state_dict(0)
+    hosts, tickets = [], []
+    for k in range(5):
+        h = torch.from_numpy(synth.body_batch(50 + k, B, L)).pin_memory()
+        hosts.append(h)
+        tickets.append(pipe.submit(h))
+        if k >= 1:                                   # consume with a lag of one, like bench.py
+            dec, probs = pipe.result(tickets[k - 1])
+            want = net.classify_ragged(state, [pp.mad_normalise(x) for x in hosts[k - 1].numpy()])
+            assert np.abs(probs[0] - want).max() < 1e-3, k
+            assert set(dec.tolist()) <= {1, 2, 3}    # length == max_len: never try_again
+    dec, probs = pipe.result(tickets[-1])
+    want = net.classify_ragged(state, [pp.mad_normalise(x) for x in hosts[-1].numpy()])
+    assert np.abs(probs[0] - want).max() < 1e-3
