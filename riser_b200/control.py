@@ -19,6 +19,7 @@ class SequencerControl():
         self.out_filename = out_file
         self.classifier = BatchedClassifier(models, processor)
         self.batch_latencies = []      # seconds from "batch in hand" to "decisions on host"
+        self.batch_sizes = []
 
     def target(self, mode, duration_h, threshold, unblock_duration=0.1):
         self.client.send_warning(
@@ -46,6 +47,7 @@ class SequencerControl():
                 res = self.classifier.classify_batch(signals, [read.id for _, read in batch],
                                                      polyA_cache, threshold, mode)
                 self.batch_latencies.append(time.monotonic() - t0)
+                self.batch_sizes.append(len(batch))
 
                 for i, (channel, read) in enumerate(batch):
                     code = int(res.decisions[i])

@@ -80,3 +80,37 @@ class SimClient:
 
     def send_warning(self, message):
         self.messages.append(message)
+
+
+class LiveSimClient(SimClient):
+    """Flow-cell-like simulation for latency runs (BASELINE config 5): ``channels``
+    pores draw reads from a pool; every poll each active read's prefix grows by ``chunk``
+    samples; when a read is finished (unblocked / stop_receiving) or runs out of signal,
+    its channel starts the next read of the pool.  Same method surface as ``Client``."""
+    def __init__(self, pool, channels, chunk, n_polls, first_len=None):
+        super().__init__(pool, chunk, n_polls, first_len=first_len)
+        self.channels = int(channels)
+        self.next_read = 0
+        self.state = {}                       # channel -> [pool index, samples exposed, read number]
+        self.read_counter = 0
+        for c in range(1, self.channels + 1):
+            self._start(c)
+
+    def _start(self, c):
+        self.read_counter += 1
+        self.state[c] = [self.next_read % len(self.reads), self.first_len, self.read_counter]
+        self.next_read += 1
+
+    def get_read_batch(self):
+        self.poll += 1
+        batch = []
+        for c in range(1, self.channels + 1):
+            idx, n, number = self.state[c]
+            rid, sig = self.reads[idx]
+            if (c, number) in self.done or n > len(sig):
+                self._start(c)
+                idx, n, number = self.state[c]
+                rid, sig = self.reads[idx]
+            batch.append((c, SimRead(f"{rid}#{number}", number, sig[:n].tobytes())))
+            self.state[c][1] = n + self.chunk
+        return batch

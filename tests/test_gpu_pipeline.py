@@ -93,7 +93,8 @@ def test_rna004_kit_and_empty_batch():
     assert np.array_equal(res.sig_len, len_o) and np.abs(res.p_on - p_on_o).max() < 1e-3
 
 
-def test_fixed_batch_pipeline_double_buffering():
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fixed_batch_pipeline_double_buffering(use_graph):
     """The overlapped host->device->host pipeline returns, for every submitted batch, what
     the oracle gives for THAT batch (slot reuse must not mix batches)."""
     import torch
@@ -102,7 +103,7 @@ def test_fixed_batch_pipeline_double_buffering():
     B, L = 6, 8615
     proc = SignalProcessor(Kit.create_from_version("RNA004"))
     clf = BatchedClassifier(models_for(["mRNA"]), proc)
-    pipe = FixedBatchPipeline(clf, B, L, 0.9, "deplete")
+    pipe = FixedBatchPipeline(clf, B, L, 0.9, "deplete", use_graph=use_graph)
     state = synth.state_dict(0)
     hosts, tickets = [], []
     for k in range(5):
