@@ -55,8 +55,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // locates the bins holding the two ranks.  Pass B (only when shift > 0): histogram of the
 // low bits inside the located bin.  Block-uniform control flow; all threads get r1, r2.
 template <class KeyFn>
-__device__ void select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32_t k2,
-                           SelectScratch& s, uint32_t& r1, uint32_t& r2) {
+__device__ int select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32_t k2,
+                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false) {
   const int tid = threadIdx.x;
   int shift = 0;
   while ((maxkey >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
@@ -92,8 +92,16 @@ __device__ void select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint3
   if (shift == 0) {
     r1 = bin1;
     r2 = bin2;
+    if (keep_prefix) {   // hist[j] <- number of keys <= j (used to get the MAD without a second pass)
+      uint32_t run = ex;
+#pragma unroll
+      for (int j = 0; j < kBinsPerThread; ++j) {
+        run += c[j];
+        s.hist[tid * kBinsPerThread + j] = run;
+      }
+    }
     __syncthreads();
-    return;
+    return 0;
   }
   const uint32_t mask = (1u << shift) - 1u;
 #pragma unroll 1
@@ -120,6 +128,7 @@ __device__ void select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint3
     if (which) r2 = s.refined; else r1 = s.refined;
   }
   __syncthreads();
+  return shift;
 }
 
 __device__ __forceinline__ double norm_value(int x, double median, double denom) {
@@ -156,20 +165,36 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     const uint4* g4 = reinterpret_cast<const uint4*>(g - a);
     uint4* s4 = reinterpret_cast<uint4*>(stage);
     int vmin = 32767, vmax = -32768;
-    for (int c = tid; c < n_chunks; c += kThreads) {
-      const int lo = 8 * c - a;
-      if (lo >= 0 && lo + 8 <= n) {
-        const uint4 v = __ldg(g4 + c);
-        s4[c] = v;
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    auto take16 = [&](const uint4& v) {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e0 = static_cast<int16_t>(w[j] & 0xffff);
-          const int e1 = static_cast<int16_t>(w[j] >> 16);
-          vmin = min(vmin, min(e0, e1));
-          vmax = max(vmax, max(e0, e1));
+      for (int j = 0; j < 4; ++j) {
+        const int e0 = static_cast<int16_t>(w[j] & 0xffff);
+        const int e1 = static_cast<int16_t>(w[j] >> 16);
+        vmin = min(vmin, min(e0, e1));
+        vmax = max(vmax, max(e0, e1));
+      }
+    };
+    // interior chunks (fully inside the window) are 16-byte loads, four in flight per thread;
+    // the (at most two) edge chunks are peeled into scalar loads
+    const int c_lo = (a > 0) ? 1 : 0;
+    const int c_hi = (a + n) >> 3;          // chunks [c_lo, c_hi) are interior
+    for (int c = c_lo + tid; c < c_hi; c += 4 * kThreads) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u * kThreads < c_hi) v[u] = __ldg(g4 + c + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u * kThreads < c_hi) {
+          s4[c + u * kThreads] = v[u];
+          take16(v[u]);
         }
-      } else {
+    }
+    if (tid < 2) {
+      const int c = tid ? c_hi : 0;
+      if ((tid == 0 && c_lo == 1) || (tid == 1 && c_hi < n_chunks && !(c_hi == 0 && c_lo == 1))) {
+        const int lo = 8 * c - a;
         for (int i = max(lo, 0); i < min(lo + 8, n); ++i) {
           const int e = g[i];
           stage[a + i] = static_cast<int16_t>(e);
@@ -196,15 +221,40 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     // ---- median: mean of the two middle order statistics -> med2 = 2 * median (exact)
     const uint32_t k1 = static_cast<uint32_t>((n - 1) >> 1), k2 = static_cast<uint32_t>(n >> 1);
     uint32_t r1, r2;
-    select_two([&](int i) { return static_cast<uint32_t>(x[i] - vmin); }, n,
-               static_cast<uint32_t>(vmax - vmin), k1, k2, s, r1, r2);
+    const int range = vmax - vmin;
+    const int shift_used = select_two([&](int i) { return static_cast<uint32_t>(x[i] - vmin); }, n,
+                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true);
     const int med2 = 2 * vmin + static_cast<int>(r1 + r2);
 
     // ---- MAD on keys d = |2x - med2| = 2|x - median| -> mad4 = 4 * MAD (exact)
     const uint32_t dmax = static_cast<uint32_t>(max(abs(2 * vmin - med2), abs(2 * vmax - med2)));
-    select_two([&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)); }, n, dmax, k1, k2,
-               s, r1, r2);
-    const uint32_t mad4 = r1 + r2;
+    uint32_t mad4;
+    if (shift_used == 0) {
+      // The value histogram already holds the whole distribution: with P[u] = #{x - vmin <= u}
+      // and m = med2 - 2*vmin, #{|2x - med2| <= d} = P[floor((m+d)/2)] - P[ceil((m-d)/2) - 1];
+      // the two middle order statistics of d are found by bisection on d (threads 0 and 1).
+      if (tid < 2) {
+        const int m = static_cast<int>(r1 + r2);
+        const uint32_t want = (tid ? k2 : k1) + 1;
+        int lo_d = 0, hi_d = static_cast<int>(dmax);
+        while (lo_d < hi_d) {
+          const int d = (lo_d + hi_d) >> 1;
+          int hi_u = (m + d) >> 1;
+          hi_u = min(hi_u, range);
+          const int lo_u = (m - d + 1) >> 1;                 // ceil((m - d) / 2), may be <= 0
+          const uint32_t cnt = s.hist[hi_u] - (lo_u > 0 ? s.hist[lo_u - 1] : 0u);
+          if (cnt >= want) hi_d = d; else lo_d = d + 1;
+        }
+        s.res[tid] = static_cast<uint32_t>(lo_d);
+      }
+      __syncthreads();
+      mad4 = s.res[0] + s.res[1];
+      __syncthreads();
+    } else {
+      select_two([&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)); }, n, dmax, k1, k2,
+                 s, r1, r2);
+      mad4 = r1 + r2;
+    }
     if (med2_mad4 && tid == 0) {
       med2_mad4[2 * b] = med2;
       med2_mad4[2 * b + 1] = static_cast<int32_t>(mad4);
@@ -240,10 +290,38 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     __syncthreads();
     const uint32_t dthr = s.refined;
     auto flagged = [&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)) > dthr; };
+    // Bulk path: (x - median) / denom == k / D with k = 2x - 2*median (an exact small integer)
+    // and D = 2 * denom (exact).  With y = RN(1/D), q0 = RN(k*y), e = k - q0*D (exact in one
+    // FMA), RN(q0 + e*y) is the correctly rounded quotient (Markstein's final division step),
+    // i.e. bit-identical to the reference's float64 divide at 3 FP64 ops instead of a full DDIV.
+    const double Dd = __dmul_rn(2.0, denom);
+    const double yrcp = __ddiv_rn(1.0, Dd);
+    auto fast_k = [&](int ki) {
+      const double k = static_cast<double>(ki);
+      const double q0 = __dmul_rn(k, yrcp);
+      const double e = __fma_rn(-q0, Dd, k);
+      return static_cast<float>(__fma_rn(e, yrcp, q0));
+    };
+    auto fast_norm = [&](int xv) { return fast_k(2 * xv - med2); };
 
     // ---- normalise + smooth, 4 samples per thread-iteration, 16-byte stores
     for (int gidx = tid; gidx < n_groups; gidx += kThreads) {
       const int i0 = 4 * gidx;
+      if (i0 + 4 <= n) {
+        // common case: four in-range samples, none an outlier -> straight-line code
+        const int k0 = 2 * x[i0] - med2, k1 = 2 * x[i0 + 1] - med2, k2 = 2 * x[i0 + 2] - med2,
+                  k3 = 2 * x[i0 + 3] - med2;
+        const uint32_t kmax = static_cast<uint32_t>(max(max(abs(k0), abs(k1)), max(abs(k2), abs(k3))));
+        if (kmax <= dthr) {
+          float4 v;
+          v.x = fast_k(k0);
+          v.y = fast_k(k1);
+          v.z = fast_k(k2);
+          v.w = fast_k(k3);
+          *reinterpret_cast<float4*>(o + i0) = v;
+          continue;
+        }
+      }
       const int cnt = min(4, n - i0);
       bool f[4];
       bool any = false;
@@ -252,12 +330,12 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
         f[e] = (e < cnt) && flagged(i0 + e);
         any |= f[e];
       }
-      if (!any && cnt == 4) {
+      if (!any && cnt == 4) {   // (kept for the slow path's bookkeeping; the common case returned above)
         float4 v;
-        v.x = static_cast<float>(norm_value(x[i0], median, denom));
-        v.y = static_cast<float>(norm_value(x[i0 + 1], median, denom));
-        v.z = static_cast<float>(norm_value(x[i0 + 2], median, denom));
-        v.w = static_cast<float>(norm_value(x[i0 + 3], median, denom));
+        v.x = fast_norm(x[i0]);
+        v.y = fast_norm(x[i0 + 1]);
+        v.z = fast_norm(x[i0 + 2]);
+        v.w = fast_norm(x[i0 + 3]);
         *reinterpret_cast<float4*>(o + i0) = v;
         continue;
       }
