@@ -85,6 +85,7 @@ struct ConvArgs {
   const float* bias;
   const int32_t* len0;
   void* out;
+  const uint8_t* flags;   // per M super-tile: 0 = every row pair lies beyond its read's valid length + 1 -> skip
   int rows_in, Lp_in, Lp_out, shift;
   int cin_p, cout_p, n_tile, n_tiles, k_blocks;
   int super0, n_supers;   // range of M super-tiles this launch covers (x n_tiles work items)
@@ -107,10 +108,19 @@ struct ConvArgs {
   float w_inv_scale;
 };
 
+struct ActivityLayer {
+  int Lp_in, rows_in, rows_per_super, shift, n_supers, flag_off;
+};
+struct ActivityArgs {
+  ActivityLayer layer[kMaxLayers];
+  int n_layers, total;
+};
+
 struct LayerPlan {
   CUtensorMap tm_a, tm_b;
   ConvArgs args;
   int n_supers_total = 0;
+  int flag_off = 0;
   size_t smem = 0;
 };
 
@@ -121,6 +131,8 @@ struct riser_plan {
   const riser_model* model = nullptr;
   int B = 0, max_len = 0;
   int fuse_l0 = 0;                      // layer 0 computed inside layer 1's kernel
+  uint8_t* flags = nullptr;             // tile activity flags (plan-owned), see tile_activity_kernel
+  riser::ActivityArgs activity;
   int chunk_reads = 0, n_chunked = 0;   // early layers 0..n_chunked-1 run chunk by chunk (L2 residency)
   int Lmax[riser::kMaxLayers + 1];
   int Lp[riser::kMaxLayers + 1];
@@ -277,6 +289,24 @@ struct ItemCursor {
       ++super;
     }
   }
+  __device__ __forceinline__ int peek_super() const {   // super-tile of the following item
+    return super + step_super + ((n + step_n >= n_tiles) ? 1 : 0);
+  }
+};
+
+// Activity flag of the current item, with the next item's flag loaded one iteration ahead so
+// that the single-thread roles never wait on it.
+struct ItemFlags {
+  const uint8_t* flags;
+  uint32_t next_flag;
+  __device__ __forceinline__ ItemFlags(const uint8_t* f, int first_super, bool any) : flags(f), next_flag(1) {
+    if (flags && any) next_flag = __ldg(flags + first_super);
+  }
+  __device__ __forceinline__ bool take(const ItemCursor& cur, bool has_next) {
+    const uint32_t now = next_flag;
+    if (flags && has_next) next_flag = __ldg(flags + cur.peek_super());
+    return now != 0;
+  }
 };
 
 template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false>
@@ -343,7 +373,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       uint32_t pa = 0, pb = 0;
       const uint32_t a_tx = kATiles * a.a_tx_bytes;
       ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+      ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
       for (int item = blockIdx.x; !FUSED && item < n_items; item += gridDim.x, cur.next()) {
+        if (!fl.take(cur, item + gridDim.x < n_items)) continue;
         const int m0 = cur.super * (MS * kBlockM) - 1;
         const int n0 = cur.n * a.n_tile;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
@@ -390,7 +422,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
       const int nk_last = (a.cin_p - (a.k_blocks - 1) * kBlockK) / 16;
       const uint32_t acc_stride = MS * a.acc_cols;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+      ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+        if (!fl.take(cur, item + gridDim.x < n_items)) continue;
         mbar_wait(&s.tmem_empty[stage], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + stage * acc_stride;
@@ -462,7 +497,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     int sa = 0;
     uint32_t pa = 0;
     ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
+    ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+      if (!fl.take(cur, item + gridDim.x < n_items)) continue;
       const int r0 = cur.super * (MS * kBlockM) - 1;
       mbar_wait(&s.a_empty[sa], pa ^ 1);
       unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroupBytes;
@@ -539,10 +576,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int i = et; i < a.n_tile; i += kEpiThreads) s.bias[0][i] = a.bias[i];
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    int stage = 0, it = 0;
+    int stage = 0, it = -1;
     uint32_t acc_phase = 0;
     ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next(), ++it) {
+    ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+      if (!fl.take(cur, item + gridDim.x < n_items)) continue;
+      ++it;
       const int m0 = cur.super * (MS * kBlockM);
       const int n0 = cur.n * a.n_tile;
       const float* bias_s = s.bias[0];
@@ -630,6 +670,28 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
   }
   if (ms == 2) return pick_conv_planes<2, false>(planes, wplanes);
   return pick_conv_planes<1, false>(planes, wplanes);
+}
+
+// ------------------------------------------------------------------------------------
+// Per-layer activity flags of the M super-tiles: a super-tile is active when at least one of
+// its row pairs has pooled index t' <= valid output length of its read (the "<=" keeps the
+// zero row that terminates every read written).  Ragged batches and skipped reads (len 0)
+// then cost only the tiles they really need.
+__global__ void tile_activity_kernel(const int32_t* __restrict__ len0, ActivityArgs aa, uint8_t* __restrict__ flags) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= aa.total) return;
+  int l = 0;
+  while (l + 1 < aa.n_layers && idx >= aa.layer[l + 1].flag_off) ++l;
+  const ActivityLayer L = aa.layer[l];
+  const int sidx = idx - L.flag_off;
+  const int row0 = sidx * L.rows_per_super;
+  const int row1 = min(row0 + L.rows_per_super, L.rows_in);
+  bool active = false;
+  for (int b = row0 / L.Lp_in; !active && static_cast<int64_t>(b) * L.Lp_in < row1; ++b) {
+    const int t_lo = max(row0 - b * L.Lp_in, 0);
+    active = (t_lo >> 1) <= (len0[b] >> L.shift);
+  }
+  flags[idx] = active ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1025,6 +1087,24 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
     lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
   }
+  // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
+  p->activity.n_layers = 0;
+  p->activity.total = 0;
+  if (env_int("RISER_TILE_SKIP", 1)) {
+    for (int i = 1; i < m->n_layers; ++i) {
+      const ConvArgs& a = p->layer[i].args;
+      ActivityLayer& al = p->activity.layer[p->activity.n_layers++];
+      al.Lp_in = a.Lp_in;
+      al.rows_in = a.rows_in;
+      al.rows_per_super = a.ms * kBlockM;
+      al.shift = a.shift;
+      al.n_supers = p->layer[i].n_supers_total;
+      al.flag_off = p->activity.total;
+      p->layer[i].flag_off = al.flag_off;
+      p->activity.total += al.n_supers;
+    }
+    RISER_CUDA_TRY(cudaMalloc(&p->flags, p->activity.total));
+  }
   for (int ms = 1; ms <= 4; ms <<= 1)
     for (int pl = 0; pl < 3; ++pl) {
       for (int res = (ms == 4 ? 1 : 0); res < 2; ++res)
@@ -1038,6 +1118,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
 }
 
 extern "C" int riser_plan_destroy(riser_plan* p) {
+  if (p) cudaFree(p->flags);
   delete p;
   return RISER_OK;
 }
@@ -1047,7 +1128,7 @@ extern "C" int riser_forward_launches(const riser_plan* p) {
   const int n = p->model->n_layers;
   const int chunks = p->n_chunked > 0 ? (p->B + p->chunk_reads - 1) / p->chunk_reads : 0;
   const int l0 = p->fuse_l0 ? (p->n_chunked > 0 ? chunks : 1) : 0;   // layer-0 launches that fusion removes
-  return chunks * p->n_chunked + (n - p->n_chunked) + 1 - l0;
+  return chunks * p->n_chunked + (n - p->n_chunked) + 1 - l0 + (p->flags ? 1 : 0);
 }
 
 extern "C" int riser_plan_fused_layer0(const riser_plan* p) { return p ? p->fuse_l0 : 0; }
@@ -1090,6 +1171,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   ConvArgs a = lp.args;
   a.len0 = len;
   const int fused = (i == 1 && p->fuse_l0) ? 1 : 0;
+  a.flags = p->flags ? p->flags + lp.flag_off : nullptr;
   if (fused) {
     RISER_REQUIRE(x, "riser_forward: null x");
     a.x = x;
@@ -1120,6 +1202,10 @@ extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* 
     RISER_REQUIRE(x, "riser_forward_stage: null x");
     RISER_REQUIRE(ld_x >= p->max_len && (ld_x & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
                   "riser_forward: x must be 8-byte aligned with even ld_x >= max_len");
+    if (p->flags) {
+      tile_activity_kernel<<<(p->activity.total + 255) / 256, 256, 0, st>>>(len, p->activity, p->flags);
+      RISER_CUDA_TRY(cudaGetLastError());
+    }
     if (p->n_chunked == 0) return launch_layer0(p, x, ld_x, len, 0, p->B, st);
     for (int b0 = 0; b0 < p->B; b0 += p->chunk_reads) {
       const int nb = std::min(p->chunk_reads, p->B - b0);

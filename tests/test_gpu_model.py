@@ -162,3 +162,36 @@ def test_decide_kernel_matches_control_rule():
                 on = [torch.tensor(probs[m, b, 1]) for m in range(M)]
                 off = [torch.tensor(probs[m, b, 0]) for m in range(M)]
                 assert got[b] == ctl.decide(on, off, int(lens[b]), 12048, thr, mode), (mode, thr, b)
+
+
+@pytest.mark.parametrize("precision", [PREC_F16, PREC_F16_X3])
+def test_plan_reuse_with_stale_activations_and_skipped_reads(precision):
+    """Tiles that lie wholly beyond a read's valid length are skipped, so the activation
+    buffers keep stale rows from earlier batches; results must not depend on them.  Batch 1
+    fills every buffer with full-length reads, batch 2 reuses the plan with short reads and
+    skipped (length 0) reads in other positions."""
+    rng = np.random.default_rng(21)
+    state = synth.state_dict(1)
+    model = Model(state, CFG, LOG, "mtRNA", precision=precision)
+    B = 10
+    first = [pp.mad_normalise(synth.body(rng, 12048)) for _ in range(B)]
+    x, lens = to_device_batch(first, ld=12048)
+    p1 = model.classify_batch(x, lens, max_len=12048).cpu().numpy()
+    assert np.abs(p1 - net.classify_ragged(state, first)).max() < PROB_TOL[precision]
+    lengths = [4096, 0, 5000, 12048, 0, 4097, 9000, 0, 6001, 4500]
+    second = [pp.mad_normalise(synth.body(rng, n)) if n else np.zeros(0) for n in lengths]
+    x2 = torch.zeros(B, 12048)
+    for b, v in enumerate(second):
+        x2[b, :len(v)] = torch.from_numpy(np.asarray(v, dtype=np.float64)).float()
+    # poison the padding beyond each read's length: it must never be read as signal
+    for b, n in enumerate(lengths):
+        x2[b, n:] = 7.5
+    lens2 = torch.tensor(lengths, dtype=torch.int32).cuda()
+    p2 = model.classify_batch(x2.cuda(), lens2, max_len=12048).cpu().numpy()
+    live = [b for b, n in enumerate(lengths) if n]
+    want = net.classify_ragged(state, [second[b] for b in live])
+    assert np.abs(p2[live] - want).max() < PROB_TOL[precision]
+    assert np.isnan(p2[[b for b, n in enumerate(lengths) if not n]]).all()
+    # and again with the long reads: buffers now hold the short batch's leftovers
+    p3 = model.classify_batch(x, lens, max_len=12048).cpu().numpy()
+    assert np.array_equal(p3, p1)
