@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .preprocess import RaggedBatch
+from .preprocess import RaggedBatch, PinnedArena
 from .model import decide, DEFAULT_CHUNK
 
 # decision codes (include/riser_b200.h)
@@ -37,6 +37,7 @@ class BatchedClassifier:
         self.fixed_trim = processor.get_fixed_trim_length()
         self.ld = (self.max_len + 3) & ~3
         self._bufs = {}
+        self._arena = PinnedArena(self.device)
 
     # ------------------------------------------------------------------ device stages
     def _buffers(self, B):
@@ -105,7 +106,7 @@ class BatchedClassifier:
             res.h2d_bytes = res.d2h_bytes = 0
             return res
         cached = np.fromiter((polyA_cache.get(r, -1) for r in read_ids), dtype=np.int32, count=B)
-        batch = RaggedBatch(signals, self.device)
+        batch = RaggedBatch(signals, self.device, arena=self._arena)
         start, length, detected = self.select_windows(batch, cached)
         decisions, probs = self.run_windows(batch, start, length, threshold, mode)
         # packed pinned result buffer: len | detected | probs | decisions (4-byte fields first)

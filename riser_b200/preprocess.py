@@ -35,27 +35,65 @@ class Kit():
             raise Exception(f"Invalid kit version {version}")
 
 
+class PinnedArena:
+    """Grow-only pinned host buffer + device buffer pair reused across batches (pinning and
+    cudaMalloc per batch would dominate the latency of a live 512-read batch)."""
+    def __init__(self, device):
+        self.device = device
+        self.capacity = 0
+        self.host = self.dev = self.meta_host = self.meta_dev = None
+        self.meta_capacity = 0
+
+    def reserve(self, n_samples, n_reads):
+        if n_samples > self.capacity:
+            self.capacity = int(n_samples * 1.25) + 4096
+            self.host = torch.empty(self.capacity, dtype=torch.int16).pin_memory()
+            self.dev = torch.empty(self.capacity, dtype=torch.int16, device=self.device)
+        if n_reads > self.meta_capacity:
+            self.meta_capacity = int(n_reads * 1.25) + 64
+            # int64 words: off [B+1] then n (int32 pairs packed) [B]
+            self.meta_host = torch.empty(2 * self.meta_capacity + 2, dtype=torch.int64).pin_memory()
+            self.meta_dev = torch.empty(2 * self.meta_capacity + 2, dtype=torch.int64, device=self.device)
+
+
 class RaggedBatch:
     """int16 reads packed back to back on the device: ``sig`` [total], ``off`` int64
     [B+1], ``n`` int32 [B].  Built from host arrays through one pinned staging
-    buffer and one H2D copy."""
-    def __init__(self, signals, device):
-        n = np.fromiter((len(s) for s in signals), dtype=np.int64, count=len(signals))
+    buffer and one H2D copy (two with metadata); pass a ``PinnedArena`` to reuse buffers."""
+    def __init__(self, signals, device, arena=None):
+        B = len(signals)
+        n = np.fromiter((len(s) for s in signals), dtype=np.int64, count=B)
         # keep every read 16-byte aligned so the kernels' vector loads need no peeling
         padded = (n + 7) & ~7
-        off = np.zeros(len(signals) + 1, dtype=np.int64)
+        off = np.zeros(B + 1, dtype=np.int64)
         np.cumsum(padded, out=off[1:])
-        host = torch.empty(int(off[-1]) + 8, dtype=torch.int16).pin_memory()
-        hv = host.numpy()
-        for s, o, k in zip(signals, off[:-1], n):
-            hv[o:o + k] = s
-        self.B = len(signals)
+        total = int(off[-1]) + 8
+        self.B = B
         self.n_host = n.astype(np.int32)
-        self.sig = host.to(device, non_blocking=True)
-        self.off = torch.from_numpy(off).to(device, non_blocking=True)
-        self.n = torch.from_numpy(self.n_host).to(device, non_blocking=True)
-        self._host = host      # keep the pinned buffer alive until the copy has run
-        self.h2d_bytes = host.numel() * 2 + off.nbytes + self.n_host.nbytes
+        if arena is None:
+            host = torch.empty(total, dtype=torch.int16).pin_memory()
+            hv = host.numpy()
+            for s, o, k in zip(signals, off[:-1], n):
+                hv[o:o + k] = s
+            self.sig = host.to(device, non_blocking=True)
+            self.off = torch.from_numpy(off).to(device, non_blocking=True)
+            self.n = torch.from_numpy(self.n_host).to(device, non_blocking=True)
+            self._host = host      # keep the pinned buffer alive until the copy has run
+        else:
+            arena.reserve(total, B)
+            hv = arena.host.numpy()
+            for s, o, k in zip(signals, off[:-1], n):
+                hv[o:o + k] = s
+            self.sig = arena.dev[:total]
+            self.sig.copy_(arena.host[:total], non_blocking=True)
+            mh = arena.meta_host.numpy()
+            mh[:B + 1] = off
+            mh[B + 1:B + 1 + (B + 1) // 2].view(np.int32)[:B] = self.n_host
+            words = B + 1 + (B + 1) // 2
+            arena.meta_dev[:words].copy_(arena.meta_host[:words], non_blocking=True)
+            self.off = arena.meta_dev[:B + 1]
+            self.n = arena.meta_dev[B + 1:words].view(torch.int32)[:B]
+        self.h2d_bytes = total * 2 + off.nbytes + self.n_host.nbytes
 
 
 class SignalProcessor():
