@@ -93,10 +93,12 @@ int riser_normalise(const int16_t* sig, const int64_t* off, const int32_t* start
  * Read b is sig[off[b] .. off[b] + n[b]).  polya_end[b] = the returned window
  * start index, or -1 for None.  Window statistics are exact integers; the
  * mean-change test is evaluated in float64 in the reference's operation order.
+ * polya_start (optional, may be NULL): the poly(A) start window the scan found, -1 for
+ * None (riser/test.py:80-117 get_polyA_coords returns both, at resolution 500 / MAD 20).
  * stats (optional, may be NULL): int32 [B, max_windows, 3] = {sum, 2*median,
  * 4*MAD} per 500-sample window.                                                */
 int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, int B,
-                    int32_t* polya_end, int32_t* stats, int max_windows,
+                    int32_t* polya_end, int32_t* polya_start, int32_t* stats, int max_windows,
                     riser_stream_t stream);
 
 /* Replaces the length gating of riser/control.py:36-60 (with preprocess.py:84-85,

@@ -20,7 +20,8 @@ SIGNATURES = {
     "riser_normalise_max_len": (c_int, []),
     "riser_normalise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_i64,
                                 c_void_p, c_void_p]),
-    "riser_polya_end": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "riser_polya_end": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p]),
     "riser_select_window": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p]),
     "riser_model_create": (c_int, [P(c_void_p), c_int, P(c_int), P(c_void_p), P(c_void_p), c_void_p,

@@ -417,7 +417,7 @@ __device__ __forceinline__ uint32_t warp_mid_sum(const uint32_t (&key)[kPerLane]
 __global__ void __launch_bounds__(kThreads)
 polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
              const int32_t* __restrict__ nsamp, int B, int32_t* __restrict__ polya_end,
-             int32_t* __restrict__ stats, int max_windows) {
+             int32_t* __restrict__ polya_start, int32_t* __restrict__ stats, int max_windows) {
   __shared__ int32_t w_sum[kMaxWindows];
   __shared__ int32_t w_mad4[kMaxWindows];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -472,6 +472,7 @@ polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
         if (pstart != 0 && pend == 0 && mad > 20.0) pend = i;
       }
       polya_end[b] = pend ? pend : -1;
+      if (polya_start) polya_start[b] = pstart ? pstart : -1;
     }
     __syncthreads();
   }
@@ -572,14 +573,14 @@ extern "C" int riser_select_window(const int32_t* n, const int32_t* cached_end, 
 }
 
 extern "C" int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, int B,
-                               int32_t* polya_end, int32_t* stats, int max_windows,
+                               int32_t* polya_end, int32_t* polya_start, int32_t* stats, int max_windows,
                                riser_stream_t stream) {
   RISER_REQUIRE(B >= 0, "riser_polya_end: B < 0");
   if (B == 0) return RISER_OK;
   RISER_REQUIRE(sig && off && n && polya_end, "riser_polya_end: null pointer");
   RISER_REQUIRE(!stats || max_windows > 0, "riser_polya_end: stats given but max_windows <= 0");
   const int grid = std::min(B, sm_count() * 4);
-  polya_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(sig, off, n, B, polya_end, stats, max_windows);
+  polya_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(sig, off, n, B, polya_end, polya_start, stats, max_windows);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

@@ -81,7 +81,8 @@ class BatchedClassifier:
         # (their prefix is skipped by giving them length 0 in the detection launch)
         n_detect = torch.where(cached >= 0, torch.zeros_like(batch.n), batch.n)
         _lib.check(L.riser_polya_end(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(n_detect), B,
-                                     _lib.ptr(buf["detected"]), None, 0, _lib.stream_ptr()), "riser_polya_end")
+                                     _lib.ptr(buf["detected"]), None, None, 0, _lib.stream_ptr()),
+                   "riser_polya_end")
         _lib.check(L.riser_select_window(_lib.ptr(batch.n), _lib.ptr(cached), _lib.ptr(buf["detected"]), B,
                                          self.min_len, self.max_len, self.fixed_trim, _lib.ptr(buf["start"]),
                                          _lib.ptr(buf["len"]), _lib.stream_ptr()), "riser_select_window")

@@ -151,14 +151,14 @@ class SignalProcessor():
             return ends[0].cpu().numpy(), ends[1].cpu().numpy()
         return ends.cpu().numpy()
 
-    def polya_end_device(self, batch, return_stats=False):
+    def polya_end_device(self, batch, return_stats=False, starts=None):
         ends = torch.empty(batch.B, dtype=torch.int32, device=batch.sig.device)
         stats, max_w = None, 0
         if return_stats:
             max_w = max(1, int(batch.n_host.max()) // _TRIM_RESOLUTION)
             stats = torch.zeros(batch.B, max_w, 3, dtype=torch.int32, device=batch.sig.device)
         _lib.check(_lib.lib().riser_polya_end(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(batch.n),
-                                              batch.B, _lib.ptr(ends), _lib.ptr(stats), max_w,
+                                              batch.B, _lib.ptr(ends), _lib.ptr(starts), _lib.ptr(stats), max_w,
                                               _lib.stream_ptr()), "riser_polya_end")
         return (ends, stats) if return_stats else ends
 

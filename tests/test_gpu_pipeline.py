@@ -118,3 +118,36 @@ def test_fixed_batch_pipeline_double_buffering(use_graph):
     dec, probs = pipe.result(tickets[-1])
     want = net.classify_ragged(state, [pp.mad_normalise(x) for x in hosts[-1].numpy()])
     assert np.abs(probs[0] - want).max() < 1e-3
+
+
+def test_offline_evaluator_matches_reference_ladder(golden_dir):
+    """riser_b200.evaluate (riser/test.py semantics) against probabilities the reference's own
+    Model.classify produced at the test.py ladder lengths 4096 / 7108 / 10120."""
+    from riser_b200 import evaluate as ev
+    g = np.load(os.path.join(golden_dir, "convnet_probs.npz"))
+    assert ev.ladder("RNA002") == [4096, 7108, 10120] and ev.ladder("RNA004") == [4096, 8096]
+    X = synth.body_batch(int(g["cfg1_seed"]), 48, 12048)
+    reads = [(f"r{i}", X[i]) for i in range(48)]
+    reads[5] = ("short", X[5][:7000])          # too short for the 7108 / 10120 steps
+    proc = SignalProcessor(Kit.create_from_version("RNA002"))
+    lines = ev.evaluate(reads, models_for(["mRNA"])[0], proc, "RNA002", already_trimmed=True,
+                        model_id="mRNA_model", dataset="synthetic", filename="x.fast5")
+    assert len(lines) == 48
+    for i, ln in enumerate(lines):
+        f = ln.rstrip("\n").split("\t")
+        assert f[:6] == ["mRNA_model", "synthetic", "x.fast5", reads[i][0], "boostnano", "boostnano"]
+        preds = f[6].split(";")
+        assert len(preds) == (1 if i == 5 else 3)
+        for j, pr in enumerate(preds):
+            n, pp_ = pr.split(":")
+            assert int(n) == int(g["cfg1_ladder"][j])
+            got = np.array([float(v) for v in pp_.split(",")])
+            assert np.abs(got - g["cfg1_probs"][i, j]).max() < 1e-3
+    # dynamic trimming path: poly(A) found -> cut at end + 1, else the fixed trim (test.py:190-198)
+    raw = synth.raw_reads(12, 10, min_body=11000, max_body=13000, frac_no_polya=0.3)
+    out = ev.evaluate(raw, models_for(["mRNA"])[0], proc, "RNA002", already_trimmed=False)
+    from oracle import preprocess_oracle as opp
+    for (rid, sig), ln in zip(raw, out):
+        f = ln.split("\t")
+        e = opp.polya_end(sig)
+        assert f[5] == str(e)
