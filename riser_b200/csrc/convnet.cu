@@ -221,15 +221,14 @@ struct ConvSmem {
   uint64_t w_full;
   uint64_t tmem_full[kMaxAccStages], tmem_empty[kMaxAccStages];
   uint32_t tmem_base;
-  float bias[2][kMaxNTile];
+  alignas(16) float bias[2][kMaxNTile];
   float4 w0q[32];        // fused layer 0: {w[c][0], w[c][1], w[c][2], bias[c]} per output channel
 };
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
-  return *reinterpret_cast<uint32_t*>(&h);
+// fp32 pair -> fp16 pair, saturated to the fp16 range (inf -> 65504) in the half2 domain
+__device__ __forceinline__ __half2 sat_half2(float a, float b) {
+  return __hmin2(__floats2half2_rn(a, b), __floats2half2_rn(65504.f, 65504.f));
 }
-
 // Epilogue for one chunk of 16 accumulator columns held one row per lane.  Rows (lanes) 2j
 // and 2j+1 are the two positions of one max-pool pair; the even lane finishes and stores
 // columns 0..7 of the chunk, the odd lane columns 8..15.
@@ -241,25 +240,38 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
   for (int j = 0; j < 8; ++j) {
     const float mine = __uint_as_float(odd ? v[j + 8] : v[j]);
     const float send = __uint_as_float(odd ? v[j] : v[j + 8]);
-    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    const float bsum = fmaf(fmaxf(mine, recv), inv_scale, bias_s[col0 + (odd ? 8 : 0) + j]);
-    r[j] = valid ? fmaxf(bsum, 0.f) : 0.f;
+    r[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));     // max-pool the row pair
   }
   if (!writable) return;
   const int c = col0 + (odd ? 8 : 0);
+  if (valid) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(r[j], inv_scale, bb[j]), 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = 0.f;
+  }
   if (out_fp32) {
     float4* o = reinterpret_cast<float4*>(static_cast<float*>(out_row) + c);
     o[0] = make_float4(r[0], r[1], r[2], r[3]);
     o[1] = make_float4(r[4], r[5], r[6], r[7]);
   } else {
     __half* oh = static_cast<__half*>(out_row) + c;
-    *reinterpret_cast<uint4*>(oh) =
-        make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
-    if (lo_plane_off) {   // residual plane: a = hi + lo, hi = fp16(a), lo = fp16(a - hi)
+    __half2 h[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] -= __half2float(__float2half_rn(fminf(r[j], 65504.f)));
-      *reinterpret_cast<uint4*>(oh + lo_plane_off) =
-          make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
+    for (int j = 0; j < 4; ++j) h[j] = sat_half2(r[2 * j], r[2 * j + 1]);
+    *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(h);
+    if (lo_plane_off) {   // residual plane: a = hi + lo, hi = fp16(a), lo = fp16(a - hi)
+      __half2 l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 back = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(r[2 * j] - back.x, r[2 * j + 1] - back.y);
+      }
+      *reinterpret_cast<uint4*>(oh + lo_plane_off) = *reinterpret_cast<const uint4*>(l);
     }
   }
 }
@@ -314,8 +326,9 @@ __global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : kConvThre
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by OFFSET (not by casting through an integer): keeps the pointer in the
+  // shared address space, so the compiler emits LDS/STS instead of generic LD/ST
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr int kATiles = MS * PLANES;                       // A tiles per K block
   // fused layer 0: one contiguous (MS*128 + 2)-row tile per plane instead of MS haloed tiles
   constexpr uint32_t kFusedTileBytes = (MS * kBlockM + 8) * 128;
@@ -493,7 +506,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                : make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("bar.sync 2, %0;" ::"n"(kCvtThreads) : "memory");
     constexpr int kRows = MS * kBlockM + 2;
-    const int live_c8 = (a.cout0 + 7) >> 3;            // 8-channel chunks that hold real channels
     int sa = 0;
     uint32_t pa = 0;
     ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
@@ -524,35 +536,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
         unsigned char* row = dst + j * 128;
         const int sw = j & 7;
+        if (!live) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            *reinterpret_cast<uint4*>(row + ((c8 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+            if (PLANES == 2) *reinterpret_cast<uint4*>(row + kFusedTileBytes + ((c8 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
+        // (FFMA2 was tried here: same FMA-pipe time, twice the weight loads -> slower.)
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
-          uint4 hv = make_uint4(0, 0, 0, 0), lv = make_uint4(0, 0, 0, 0);
-          if (live && c8 < live_c8) {
-            uint32_t hi[4], lo[4];
+          __half2 hv[4], lv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v[2];
+          for (int e = 0; e < 4; ++e) {
+            float v[2] = {0.f, 0.f};
+            if (c8 * 8 + 2 * e < a.cout0) {          // uniform: skips the zero-padded channels
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 const float4 w = s.w0q[c8 * 8 + 2 * e + h];
                 const float y0 = fmaf(w.z, x1, fmaf(w.y, x0, fmaf(w.x, xm1, w.w)));
                 const float y1 = fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w)));
-                v[h] = fminf(fmaxf(fmaxf(y0, y1), 0.f), 65504.f);
-              }
-              const __half2 hh = __floats2half2_rn(v[0], v[1]);
-              hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              if (PLANES == 2) {
-                const float2 back = __half22float2(hh);
-                const __half2 hl = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
-                lo[e] = *reinterpret_cast<const uint32_t*>(&hl);
+                v[h] = fmaxf(fmaxf(y0, y1), 0.f);
               }
             }
-            hv = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (PLANES == 2) lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            hv[e] = sat_half2(v[0], v[1]);
+            if (PLANES == 2) {
+              const float2 back = __half22float2(hv[e]);
+              lv[e] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+            }
           }
           const int off = (c8 ^ sw) << 4;
-          *reinterpret_cast<uint4*>(row + off) = hv;
-          if (PLANES == 2) *reinterpret_cast<uint4*>(row + kFusedTileBytes + off) = lv;
+          *reinterpret_cast<uint4*>(row + off) = *reinterpret_cast<const uint4*>(hv);
+          if (PLANES == 2) *reinterpret_cast<uint4*>(row + kFusedTileBytes + off) = *reinterpret_cast<const uint4*>(lv);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA
