@@ -320,6 +320,8 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                         "executed_tflops": achieved * {0: 1, 1: 2, 2: 3}[precision],
+                         "executed_note": "tcgen05 passes per algorithmic FLOP: 1 (F16), 2 (F16_W2), 3 (F16_X3)",
                          "share_of_step": conv_ms / (total_ms / args.steps)},
             "e2e": {"value": reads / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
