@@ -181,6 +181,29 @@ int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows
 int riser_decide(const float* probs, const int32_t* len, int B, int M, float thr, int mode,
                  int max_len, uint8_t* decision, riser_stream_t stream);
 
+/* ------------------------------------------------------------------ ResNet variant
+ * riser/nets/resnet.py (selectable only in train.py:177-178; no shipped config or weights).
+ * Generic fp32 building blocks on CUDA cores, channel-last activations [B][L_pad][C], per-read
+ * valid lengths; BatchNorm is folded into w / bias by the host (riser_b200/resnet.py).      */
+
+/* Conv1d(Cin->Cout, K, stride, padding) [+ residual] [+ ReLU] -- resnet.py:26-43,79-81.
+ * w is packed [K][Cin][Cout]; rows outside [0, len_in[b]) are zero padding; rows
+ * t >= len_out[b] are not written.  residual (optional) has the output's layout.          */
+int riser_conv1d_cl(const float* in, const int32_t* len_in, const float* w, const float* bias,
+                    const float* residual, float* out, const int32_t* len_out, int B, int Lin_pad,
+                    int Lout_pad, int Cin, int Cout, int K, int stride, int pad, int relu,
+                    riser_stream_t stream);
+
+/* MaxPool1d(kernel 2, stride 2, padding 1) -- resnet.py:83.                                 */
+int riser_maxpool1d_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out,
+                       int B, int Lin_pad, int Lout_pad, int C, riser_stream_t stream);
+
+/* AdaptiveAvgPool1d(1) + Flatten + Linear(C, n_classes) + softmax -- resnet.py:94-98,
+ * model.py:27.  probs [B][n_classes]; NaN for len 0.                                        */
+int riser_gap_linear_softmax(const float* in, const int32_t* len, const float* fc_w, const float* fc_b,
+                             float* probs, int B, int L_pad, int C, int n_classes,
+                             riser_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,8 @@ from .model import Model, decide, PREC_F16, PREC_F16_W2, PREC_F16_X3   # noqa: F
 
 from .pipeline import BatchedClassifier, FixedBatchPipeline     # noqa: F401,E402
 from .control import SequencerControl                           # noqa: F401,E402
+from .resnet import ResNetModel                                 # noqa: F401,E402
 
 __all__ = ["Kit", "SignalProcessor", "RaggedBatch", "Model", "decide", "PREC_F16", "PREC_F16_W2", "PREC_F16_X3",
-           "BatchedClassifier", "FixedBatchPipeline", "SequencerControl"]
+           "BatchedClassifier", "FixedBatchPipeline", "SequencerControl",
+           "ResNetModel"]

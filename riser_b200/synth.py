@@ -143,3 +143,69 @@ def save_state_dict(seed, path):
     import torch
     torch.save(state_dict(seed), path)
     return path
+
+
+# ---------------------------------------------------------------- ResNet variant (riser/nets/resnet.py)
+RESNET_CONFIGS = {
+    # the reference ships no resnet config; these two exercise both block types.
+    # decoder_scale / decoder_centre: calibrated once with the reference (seed 0, 48 ragged
+    # reads) so that the logit difference is centred with a spread of ~2 -> probabilities
+    # span (0, 1) instead of saturating.
+    "basic": dict(channels=[20, 30, 45, 67], kernel=19, stride=3, padding=5, block="basic", n_layers=4,
+                  blocks=[2, 2, 2, 2], n_classes=2, decoder_scale=0.5, decoder_centre=102.62 / 3.0),
+    "bottleneck": dict(channels=[32, 64, 128, 256], kernel=19, stride=3, padding=5, block="bottleneck",
+                       n_layers=4, blocks=[1, 2, 2, 1], n_classes=2, decoder_scale=3.0,
+                       decoder_centre=-14.91 * 2.0),
+}
+
+
+def resnet_state_dict(cfg, seed, as_torch=True):
+    """Seeded state-dict with the reference ResNet's key names and shapes (resnet.py:7-131):
+    kaiming-like conv weights, non-trivial BatchNorm affine parameters and running statistics
+    (so that BN folding is really tested), unused shortcut parameters included exactly as the
+    reference constructs them (resnet.py:21-24)."""
+    rng = np.random.Generator(np.random.PCG64(5000 + seed))
+    sd = {}
+
+    def conv(name, cout, cin, k, bias=False):
+        sd[name + ".weight"] = rng.normal(0.0, np.sqrt(2.0 / (cin * k)), size=(cout, cin, k)).astype(np.float32)
+        if bias:
+            sd[name + ".bias"] = rng.normal(0.0, 0.05, size=(cout,)).astype(np.float32)
+
+    def bn(name, c):
+        sd[name + ".weight"] = rng.uniform(0.6, 1.4, size=(c,)).astype(np.float32)
+        sd[name + ".bias"] = rng.normal(0.0, 0.1, size=(c,)).astype(np.float32)
+        sd[name + ".running_mean"] = rng.normal(0.0, 0.2, size=(c,)).astype(np.float32)
+        sd[name + ".running_var"] = rng.uniform(0.5, 1.5, size=(c,)).astype(np.float32)
+        sd[name + ".num_batches_tracked"] = np.array(100, dtype=np.int64)
+
+    ch = cfg["channels"]
+    conv("conv_block.0", ch[0], 1, cfg["kernel"], bias=True)
+    bn("conv_block.1", ch[0])
+    cin = ch[0]
+    for i in range(cfg["n_layers"]):
+        cout = ch[i]
+        for j in range(cfg["blocks"][i]):
+            p = f"layers.{i}.{j}"
+            if cfg["block"] == "bottleneck":
+                mid = cout // 4
+                conv(p + ".blocks.0.0", mid, cin, 1); bn(p + ".blocks.0.1", mid)
+                conv(p + ".blocks.1.0", mid, mid, 3); bn(p + ".blocks.1.1", mid)
+                conv(p + ".blocks.2.0", cout, mid, 1); bn(p + ".blocks.2.1", cout)
+            else:
+                conv(p + ".blocks.0.0", cout, cin, 3); bn(p + ".blocks.0.1", cout)
+                conv(p + ".blocks.1.0", cout, cout, 3); bn(p + ".blocks.1.1", cout)
+            conv(p + ".shortcut.0", cout, cin, 1); bn(p + ".shortcut.1", cout)
+            cin = cout
+    # zero-sum rows and a small scale keep the logits O(1) (post-ReLU features have a large common
+    # mean), so that probabilities are not saturated and parity tests mean something
+    wdec = rng.normal(0.0, 1.0, size=(cfg["n_classes"], ch[-1]))
+    wdec -= wdec.mean(axis=1, keepdims=True)
+    sd["decoder.2.weight"] = (wdec * cfg.get("decoder_scale", 0.3) / np.sqrt(ch[-1])).astype(np.float32)
+    bias = rng.normal(0.0, 0.1, size=(cfg["n_classes"],))
+    bias[1] -= cfg.get("decoder_centre", 0.0)
+    sd["decoder.2.bias"] = bias.astype(np.float32)
+    if as_torch:
+        import torch
+        sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    return sd

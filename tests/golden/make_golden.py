@@ -266,6 +266,27 @@ def control_scenario():
     np.savez_compressed(os.path.join(GOLD, "control_scenario.npz"), **out)
 
 
+# ---------------------------------------------------------------- F. ResNet variant (nets/resnet.py)
+def resnet_goldens():
+    """The reference's own ResNet module (eval mode) on seeded weights with non-trivial BatchNorm
+    statistics; the reference ships no config for it, so both block types are exercised with
+    the configurations in riser_b200.synth.RESNET_CONFIGS."""
+    proc = proc_for("RNA002")
+    bodies = synth.ragged_bodies(321, 24, 4096, 12048)
+    normed = [np.asarray(proc.mad_normalise(b)) for b in bodies]
+    out = {"seed": np.array(321), "lengths": np.array([len(b) for b in bodies])}
+    for name, cfg in synth.RESNET_CONFIGS.items():
+        m = ref.ResNet(refshim.AttrDict(cfg)).eval()
+        sd = synth.resnet_state_dict(cfg, 0)
+        assert set(sd) == set(m.state_dict())
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            probs = np.stack([F.softmax(m(torch.from_numpy(x).float()[None]), dim=1)[0].numpy() for x in normed])
+        out[f"probs_{name}"] = probs.astype(np.float32)
+        print(f"resnet {name}: p_on range {probs[:, 1].min():.3f}..{probs[:, 1].max():.3f}")
+    np.savez_compressed(os.path.join(GOLD, "resnet_probs.npz"), **out)
+
+
 if __name__ == "__main__":
     logging.basicConfig(level=logging.WARNING)
     torch.set_num_threads(8)
@@ -276,4 +297,5 @@ if __name__ == "__main__":
         fit_heads()
     model_goldens(bodies, normed)
     control_scenario()
+    resnet_goldens()
     print("done")

@@ -150,3 +150,15 @@ def test_control_scenario(golden_dir, mode):
         assert np.abs(np.array(po) - np.array(wp)).max() < 1e-6
     assert sorted(map(tuple, g[f"unblocked_{mode}"])) == sorted(client.unblocked)
     assert sorted(map(tuple, g[f"finished_{mode}"])) == sorted(client.finished)
+
+
+def test_resnet_oracle_against_reference_golden(golden_dir):
+    from oracle import resnet_oracle as ro
+    g = np.load(os.path.join(golden_dir, "resnet_probs.npz"))
+    bodies = synth.ragged_bodies(int(g["seed"]), 24, 4096, 12048)
+    assert [len(b) for b in bodies] == list(g["lengths"])
+    for name, cfg in synth.RESNET_CONFIGS.items():
+        sd = synth.resnet_state_dict(cfg, 0)
+        for i in (0, 5, 11, 23):
+            p = ro.classify(sd, cfg, pp.mad_normalise(bodies[i])).numpy()
+            assert np.abs(p - g[f"probs_{name}"][i]).max() < 1e-6, (name, i)
