@@ -86,8 +86,13 @@ int riser_normalise(const int16_t* sig, const int64_t* off, const int32_t* start
                     const int32_t* len, int B, int max_len, float* out, int64_t ld_out,
                     int32_t* med2_mad4, riser_stream_t stream);
 
-/* Same for fp32 input (the pA-scaled path of riser/retrain/preprocess.py:36-44):
- * NOT implemented in this round; declared so the binding is stable.            */
+/* float32 variant for the training-data preparation path: replaces mad_normalise /
+ * smooth_outliers / calculate_mad / normalise of riser/retrain/preprocess.py:8-44, where the
+ * input is the pA-scaled float32 signal and numpy keeps every step in float32 (no MAD == 0
+ * guard: IEEE inf / nan as numpy gives).  Read b is sig[off[b] .. off[b] + len[b]).         */
+int riser_normalise_f32_max_len(void);
+int riser_normalise_f32(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
+                        float outlier_lim, float* out, int64_t ld_out, riser_stream_t stream);
 
 /* Replaces SignalProcessor.get_polyA_end (riser/preprocess.py:42-79), batched.
  * Read b is sig[off[b] .. off[b] + n[b]).  polya_end[b] = the returned window

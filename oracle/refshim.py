@@ -45,6 +45,21 @@ def load():
                                  ConvNet=ConvNet, ResNet=ResNet)
 
 
+def load_retrain_preprocess():
+    """riser/retrain/preprocess.py (its ont_fast5_api import is stubbed: only the arithmetic
+    functions are used)."""
+    import importlib.util
+    for name in ("ont_fast5_api", "ont_fast5_api.fast5_interface"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["ont_fast5_api.fast5_interface"].get_fast5_file = lambda *a, **k: None
+    spec = importlib.util.spec_from_file_location(
+        "riser_retrain_preprocess", os.path.join(REF_ROOT, "riser", "retrain", "preprocess.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cnn_config():
     """riser/model/*_config_*.yaml:6-12 (identical in all shipped configs)."""
     import yaml

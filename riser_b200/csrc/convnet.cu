@@ -517,23 +517,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroupBytes;
       for (int j = ct; j < kRows; j += kCvtThreads) {
         const int r = r0 + j;
-        float xm1 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f;
-        bool live = false;
-        if (r >= 0 && r < a.rows_in) {
-          const uint32_t pidx = static_cast<uint32_t>(r) >> 1;
-          const int b = static_cast<int>((static_cast<unsigned long long>(pidx) * a.pair_magic) >> 40);
-          const int tp = r - b * a.Lp_in;
-          const int L = __ldg(a.len0 + b);
-          if (tp < (L >> 1)) {
-            live = true;
-            const float* xr = a.x + static_cast<long long>(b) * a.ld_x + 2 * tp;
-            const float2 x01 = __ldg(reinterpret_cast<const float2*>(xr));
-            x0 = x01.x;
-            x1 = x01.y;
-            xm1 = (tp > 0) ? __ldg(xr - 1) : 0.f;
-            x2 = (2 * tp + 2 < L) ? __ldg(xr + 2) : 0.f;
-          }
-        }
+        // all global loads of the row are issued together (none depends on another's result);
+        // validity is applied afterwards
+        const bool inb = (r >= 0 && r < a.rows_in);
+        const uint32_t pidx = static_cast<uint32_t>(inb ? r : 0) >> 1;
+        const int b = static_cast<int>((static_cast<unsigned long long>(pidx) * a.pair_magic) >> 40);
+        const int tp = (inb ? r : 0) - b * a.Lp_in;
+        const float* xr = a.x + static_cast<long long>(b) * a.ld_x + 2 * tp;
+        const bool in_row = inb && (2 * tp + 1 < a.ld_x);
+        const int L = inb ? __ldg(a.len0 + b) : 0;
+        const float2 x01 = in_row ? __ldg(reinterpret_cast<const float2*>(xr)) : make_float2(0.f, 0.f);
+        float xm1 = (in_row && tp > 0) ? __ldg(xr - 1) : 0.f;
+        float x2 = (in_row && 2 * tp + 2 < a.ld_x) ? __ldg(xr + 2) : 0.f;
+        const float x0 = x01.x, x1 = x01.y;
+        const bool live = in_row && tp < (L >> 1);
+        if (2 * tp + 2 >= L) x2 = 0.f;
         unsigned char* row = dst + j * 128;
         const int sw = j & 7;
         if (!live) {

@@ -287,6 +287,35 @@ def resnet_goldens():
     np.savez_compressed(os.path.join(GOLD, "resnet_probs.npz"), **out)
 
 
+# ---------------------------------------------------------------- G. retrain/preprocess.py (float32 path)
+def retrain_goldens():
+    from oracle import retrain_oracle as rt
+    rp = refshim.load_retrain_preprocess()
+    rng = np.random.Generator(np.random.PCG64(77))
+    digests, lengths = [], []
+    edge_in, edge_out = {}, {}
+    bodies = synth.ragged_bodies(555, 16, 4096, 12048)
+    for k, raw in enumerate(bodies):
+        pa = rt.pa_signal(raw, scale=0.1 + 0.01 * k, offset=3.0 * k - 10)
+        digests.append(sha(rp.mad_normalise(pa.copy(), 3.5)))
+        lengths.append(len(pa))
+    cases = {"even_small": rng.normal(80, 9, size=4096), "odd_small": rng.normal(80, 9, size=4097),
+             "ties": np.round(rng.normal(80, 2, size=5000)), "constant": np.full(4500, 71.25),
+             "negative": rng.normal(-30, 4, size=6000), "tiny": np.array([1.5, 2.5, 9.0, 2.0, 1.0])}
+    spiky = rng.normal(80, 5, size=5000)
+    spiky[0] += 90; spiky[-1] -= 90; spiky[100:104] += 70; spiky[200] -= 60; spiky[201] += 60
+    cases["end_outliers_runs"] = spiky
+    for name, v in cases.items():
+        x = np.asarray(v, dtype=np.float32)
+        with np.errstate(all="ignore"):
+            y = rp.mad_normalise(x.copy(), 3.5)
+        edge_in[name], edge_out[name] = x, np.asarray(y)
+    np.savez_compressed(os.path.join(GOLD, "retrain_norm.npz"), seed=np.array(555), lengths=np.array(lengths),
+                        sha=np.stack(digests), names=np.array(sorted(cases)),
+                        **{f"in_{k}": v for k, v in edge_in.items()}, **{f"out_{k}": v for k, v in edge_out.items()})
+    print("retrain goldens:", len(digests), "reads +", len(cases), "edge cases")
+
+
 if __name__ == "__main__":
     logging.basicConfig(level=logging.WARNING)
     torch.set_num_threads(8)
@@ -298,4 +327,5 @@ if __name__ == "__main__":
     model_goldens(bodies, normed)
     control_scenario()
     resnet_goldens()
+    retrain_goldens()
     print("done")

@@ -143,3 +143,27 @@ def test_polya_random_vs_oracle(proc):
     ends = proc.get_polyA_end_batch(sigs)
     want = [(-1 if pp.polya_end(s) is None else pp.polya_end(s)) for s in sigs]
     assert list(ends) == want
+
+
+def test_retrain_float32_normalise_bit_exact(golden_dir):
+    """csrc/normalise_f32.cu against the reference's riser/retrain/preprocess.py outputs."""
+    from oracle import retrain_oracle as rt
+    from riser_b200 import retrain
+    g = np.load(os.path.join(golden_dir, "retrain_norm.npz"))
+    bodies = synth.ragged_bodies(int(g["seed"]), 16, 4096, 12048)
+    sigs = [rt.pa_signal(raw, scale=0.1 + 0.01 * k, offset=3.0 * k - 10) for k, raw in enumerate(bodies)]
+    out, _ = retrain.mad_normalise_f32_batch(sigs)
+    out = out.cpu().numpy()
+    for k, s in enumerate(sigs):
+        assert np.array_equal(sha(out[k, :len(s)]), g["sha"][k]), k
+    names = [str(n) for n in g["names"]]
+    out, _ = retrain.mad_normalise_f32_batch([g[f"in_{n}"] for n in names])
+    out = out.cpu().numpy()
+    for k, n in enumerate(names):
+        want = g[f"out_{n}"]
+        assert np.array_equal(out[k, :len(want)], want, equal_nan=True), n
+    # retrain/preprocess.py main(): cutoff, discard, stack
+    reads = [rt.pa_signal(synth.body(np.random.default_rng(i), 5000 + 900 * i)) for i in range(6)]
+    data, dropped = retrain.preprocess_reads(reads, n_secs=2, freq=3012)
+    assert data.shape == (4, 6024) and dropped == 2
+    assert np.array_equal(data[0], rt.mad_normalise(reads[2][:6024]))

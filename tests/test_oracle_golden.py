@@ -162,3 +162,16 @@ def test_resnet_oracle_against_reference_golden(golden_dir):
         for i in (0, 5, 11, 23):
             p = ro.classify(sd, cfg, pp.mad_normalise(bodies[i])).numpy()
             assert np.abs(p - g[f"probs_{name}"][i]).max() < 1e-6, (name, i)
+
+
+def test_retrain_oracle_bit_exact_against_reference(golden_dir):
+    from oracle import retrain_oracle as rt
+    g = np.load(os.path.join(golden_dir, "retrain_norm.npz"))
+    bodies = synth.ragged_bodies(int(g["seed"]), 16, 4096, 12048)
+    for k, raw in enumerate(bodies):
+        pa = rt.pa_signal(raw, scale=0.1 + 0.01 * k, offset=3.0 * k - 10)
+        assert np.array_equal(sha(rt.mad_normalise(pa)), g["sha"][k]), k
+    for name in g["names"]:
+        got, want = rt.mad_normalise(g[f"in_{name}"]), g[f"out_{name}"]
+        assert got.dtype == want.dtype == np.float32
+        assert np.array_equal(got, want, equal_nan=True), name
