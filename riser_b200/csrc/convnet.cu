@@ -96,7 +96,8 @@ struct ConvArgs {
   int a_stages, b_stages, acc_stages, resident;
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
-  int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x 128)
+  int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
+  int k32;                // 1 = 32-channel K blocks: 64-byte rows, SWIZZLE_64B (else 64 / 128 B / SWIZZLE_128B)
   // fused layer 0 (layer 1 only): A tiles are computed in-kernel from the normalised signal
   const float* x;
   long long ld_x;
@@ -209,7 +210,6 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
 // being used by every sub-tile and plane before it is released.
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = two epilogue
 // sets (each covers the four TMEM lane quadrants; the sets split the 16-column chunks).
-constexpr int kATileBytes = 136 * 128;      // smem stride of one A tile, multiple of 1024
 constexpr int kMaxAStages = 8, kMaxBStages = 8, kMaxAccStages = 4;
 constexpr int kConvThreads = 320;
 constexpr int kCvtThreads = 288;         // fused layer 0: converter warps 10..18 (514 rows = 2 passes)
@@ -276,10 +276,14 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
   }
 }
 
-// Descriptor for a K-major SWIZZLE_128B tile at shared address `addr` (< 256 KB).
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
-  constexpr uint64_t kHi = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
-                           (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+// Descriptor for a K-major swizzled tile at shared address `addr` (< 256 KB): rows of 128 bytes
+// with SWIZZLE_128B (8-row atoms of 1024 B, layout type 2), or -- K32 -- rows of 64 bytes with
+// SWIZZLE_64B (8-row atoms of 512 B, layout type 4).
+template <bool K32>
+__device__ __forceinline__ uint64_t sw_desc(uint32_t addr) {
+  constexpr uint64_t kHi = (static_cast<uint64_t>(1) << 16) |
+                           (static_cast<uint64_t>((K32 ? 512 : 1024) >> 4) << 32) |
+                           (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(K32 ? 4 : 2) << 61);
   return kHi | static_cast<uint64_t>(addr >> 4);
 }
 
@@ -321,7 +325,7 @@ struct ItemFlags {
   }
 };
 
-template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false>
+template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false, bool K32 = false>
 __global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const ConvArgs a) {
@@ -331,9 +335,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr int kATiles = MS * PLANES;                       // A tiles per K block
   // fused layer 0: one contiguous (MS*128 + 2)-row tile per plane instead of MS haloed tiles
-  constexpr uint32_t kFusedTileBytes = (MS * kBlockM + 8) * 128;
-  constexpr uint32_t kAGroupBytes = FUSED ? PLANES * kFusedTileBytes : kATiles * kATileBytes;
-  const uint32_t b_bytes = a.n_tile * kBlockK * 2;
+  constexpr int kRowBytes = K32 ? 64 : 128;                  // bytes per operand row (one K block)
+  constexpr int kKElems = kRowBytes / 2;                     // fp16 elements per K block
+  constexpr uint32_t kATile = 136 * kRowBytes;               // smem stride of one haloed A tile
+  constexpr uint32_t kFusedTileBytes = (MS * kBlockM + 8) * kRowBytes;
+  constexpr uint32_t kAGroupBytes = FUSED ? PLANES * kFusedTileBytes : kATiles * kATile;
+  const uint32_t b_bytes = a.n_tile * kRowBytes;
   unsigned char* a_ring = base;
   unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroupBytes;
   const size_t b_region_bytes = RESIDENT ? static_cast<size_t>(WPLANES) * 3 * a.k_blocks * b_bytes
@@ -380,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int tap = 0; tap < 3; ++tap)
             for (int kb = 0; kb < a.k_blocks; ++kb)
               tma_load_2d(b_region + static_cast<size_t>((wp * 3 + tap) * a.k_blocks + kb) * b_bytes, &tm_b,
-                          &s.w_full, kb * kBlockK, (wp * 3 + tap) * a.cout_p);
+                          &s.w_full, kb * kKElems, (wp * 3 + tap) * a.cout_p);
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -399,8 +406,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int ms = 0; ms < MS; ++ms)
 #pragma unroll
             for (int ap = 0; ap < PLANES; ++ap)
-              tma_load_2d(dst + (ms * PLANES + ap) * kATileBytes, &tm_a, &s.a_full[sa],
-                          ap * a.cin_p + kb * kBlockK, m0 + ms * kBlockM);
+              tma_load_2d(dst + (ms * PLANES + ap) * kATile, &tm_a, &s.a_full[sa],
+                          ap * a.cin_p + kb * kKElems, m0 + ms * kBlockM);
           if (++sa == a.a_stages) {
             sa = 0;
             pa ^= 1;
@@ -412,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               for (int wp = 0; wp < WPLANES; ++wp) {
                 mbar_wait(&s.b_empty[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&s.b_full[sb], b_bytes);
-                tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * kBlockK,
+                tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * kKElems,
                             (wp * 3 + tap) * a.cout_p + n0);
                 if (++sb == a.b_stages) {
                   sb = 0;
@@ -433,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       int sa = 0, sb = 0, stage = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
       const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
-      const int nk_last = (a.cin_p - (a.k_blocks - 1) * kBlockK) / 16;
+      const int nk_last = (a.cin_p - (a.k_blocks - 1) * kKElems) / 16;
       const uint32_t acc_stride = MS * a.acc_cols;
       ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
       ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
@@ -443,7 +450,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tc_fence_after();
         const uint32_t d_base = tmem_base + stage * acc_stride;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
-          const int nk = (kb == a.k_blocks - 1) ? nk_last : (kBlockK / 16);
+          const int nk = (kb == a.k_blocks - 1) ? nk_last : (kKElems / 16);
           mbar_wait(&s.a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_addr = a_ring_addr + sa * kAGroupBytes;
@@ -459,15 +466,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 tc_fence_after();
                 b_addr = b_region_addr + sb * b_bytes;
               }
-              const uint64_t db = sw128_desc(b_addr);
+              const uint64_t db = sw_desc<K32>(b_addr);
 #pragma unroll
               for (int ms = 0; ms < MS; ++ms) {
 #pragma unroll
                 for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {   // W_lo only meets the hi plane
-                  const uint64_t da = FUSED ? sw128_desc(a_addr + ap * kFusedTileBytes + (ms * kBlockM + tap) * 128)
-                                            : sw128_desc(a_addr + (ms * PLANES + ap) * kATileBytes + tap * 128);
+                  const uint64_t da =
+                      FUSED ? sw_desc<K32>(a_addr + ap * kFusedTileBytes + (ms * kBlockM + tap) * kRowBytes)
+                            : sw_desc<K32>(a_addr + (ms * PLANES + ap) * kATile + tap * kRowBytes);
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
+                  for (int k = 0; k < kKElems / 16; ++k)
                     if (k < nk)
                       umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
                                (kb | tap | wp | ap | k) != 0);
@@ -499,7 +507,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===================== fused layer 0: converter warps 10..17 =====================
     // Compute layer 1's A operand (layer 0 = Conv1d(1->C0,k3,same)+ReLU+MaxPool(2,2), fp32 on
     // CUDA cores, nets/cnn.py:55-64) straight into shared memory in the SWIZZLE_128B K-major
-    // layout the MMA reads: row j of the tile at byte j*128, 16-byte chunk c at (c ^ (j & 7)).
+    // layout the MMA reads: row j of the tile at byte j*128, 16-byte chunk c at (c ^ (j & 7))
+    // (K32: 64-byte rows, chunk c at (c ^ ((j >> 1) & 3)) -- SWIZZLE_64B).
     const int ct = threadIdx.x - kConvThreads;
     for (int c = ct; c < 32; c += kCvtThreads)
       s.w0q[c] = (c < a.cout0) ? make_float4(a.w0[c * 3], a.w0[c * 3 + 1], a.w0[c * 3 + 2], a.b0[c])
@@ -532,8 +541,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const float x0 = x01.x, x1 = x01.y;
         const bool live = in_row && tp < (L >> 1);
         if (2 * tp + 2 >= L) x2 = 0.f;
-        unsigned char* row = dst + j * 128;
-        const int sw = j & 7;
+        unsigned char* row = dst + j * kRowBytes;
+        const int sw = K32 ? ((j >> 1) & 3) : (j & 7);      // 16-byte-chunk XOR of the row (SWIZZLE_64B / _128B)
         if (!live) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
@@ -659,31 +668,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvArgs);
 
-template <int MS, bool RESIDENT>
+template <int MS, bool RESIDENT, bool FUSED, bool K32>
 ConvKernelFn pick_conv_planes(int planes, int wplanes) {
-  if (planes == 1 && wplanes == 1) return conv_tc_kernel<MS, 1, 1, RESIDENT>;
-  if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, RESIDENT>;
-  return conv_tc_kernel<MS, 2, 2, RESIDENT>;
+  if (planes == 1 && wplanes == 1) return conv_tc_kernel<MS, 1, 1, RESIDENT, FUSED, K32>;
+  if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, RESIDENT, FUSED, K32>;
+  return conv_tc_kernel<MS, 2, 2, RESIDENT, FUSED, K32>;
 }
-template <int MS>
-ConvKernelFn pick_conv_fused(int planes, int wplanes) {
-  if (planes == 1 && wplanes == 1) return conv_tc_kernel<MS, 1, 1, true, true>;
-  if (planes == 1 && wplanes == 2) return conv_tc_kernel<MS, 1, 2, true, true>;
-  return conv_tc_kernel<MS, 2, 2, true, true>;
-}
-ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0) {
+template <bool K32>
+ConvKernelFn pick_conv_k(int ms, int planes, int wplanes, int resident, int fused) {
   if (fused) {
-    if (ms == 4) return pick_conv_fused<4>(planes, wplanes);
-    if (ms == 2) return pick_conv_fused<2>(planes, wplanes);
-    return pick_conv_fused<1>(planes, wplanes);
+    if (ms == 4) return pick_conv_planes<4, true, true, K32>(planes, wplanes);
+    if (ms == 2) return pick_conv_planes<2, true, true, K32>(planes, wplanes);
+    return pick_conv_planes<1, true, true, K32>(planes, wplanes);
   }
   if (resident) {
-    if (ms == 4) return pick_conv_planes<4, true>(planes, wplanes);
-    if (ms == 2) return pick_conv_planes<2, true>(planes, wplanes);
-    return pick_conv_planes<1, true>(planes, wplanes);
+    if (ms == 4) return pick_conv_planes<4, true, false, K32>(planes, wplanes);
+    if (ms == 2) return pick_conv_planes<2, true, false, K32>(planes, wplanes);
+    return pick_conv_planes<1, true, false, K32>(planes, wplanes);
   }
-  if (ms == 2) return pick_conv_planes<2, false>(planes, wplanes);
-  return pick_conv_planes<1, false>(planes, wplanes);
+  if (ms == 4) return pick_conv_planes<4, false, false, K32>(planes, wplanes);
+  if (ms == 2) return pick_conv_planes<2, false, false, K32>(planes, wplanes);
+  return pick_conv_planes<1, false, false, K32>(planes, wplanes);
+}
+ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0, int k32 = 0) {
+  return k32 ? pick_conv_k<true>(ms, planes, wplanes, resident, fused)
+             : pick_conv_k<false>(ms, planes, wplanes, resident, fused);
 }
 
 // ------------------------------------------------------------------------------------
@@ -808,17 +817,18 @@ int get_encode_fn(EncodeTiledFn* fn) {
   return RISER_OK;
 }
 
-// fp16 [rows][cols] row-major, box (64 cols = 128 B, box_rows), SWIZZLE_128B, zero OOB fill
-int make_tmap(CUtensorMap* tm, void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+// fp16 [rows][cols] row-major, zero OOB fill; box (64 cols = 128 B, box_rows) with SWIZZLE_128B,
+// or (k32) box (32 cols = 64 B, box_rows) with SWIZZLE_64B
+int make_tmap(CUtensorMap* tm, void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows, bool k32 = false) {
   EncodeTiledFn enc;
   int st = get_encode_fn(&enc);
   if (st) return st;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(k32 ? 32 : kBlockK), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(RISER_ECUDA, "cuTensorMapEncodeTiled failed (%d) for %llu x %llu box %u", static_cast<int>(r),
@@ -1015,9 +1025,14 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const int rows_in = B * p->Lp[i];
     const bool last = (i == m->n_layers - 1);
     const int a_box_rows = env_int("RISER_A_BOX_ROWS", 136);   // 130 needed; a multiple of 8 is what TMA likes
+    // 32-channel K blocks (64-byte rows, SWIZZLE_64B) for narrow layers: no zero-filled half rows,
+    // twice the pipeline depth / sub-tiles per item in the same shared memory
+    const bool k32 = L.cin_p <= env_int("RISER_K32_MAX_CIN", 80);
+    const int row_bytes = k32 ? 64 : 128;
+    const int k_elems = row_bytes / 2;
     int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
-                       a_box_rows);
-    if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile);
+                       a_box_rows, k32);
+    if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile, k32);
     if (st) {
       delete p;
       return st;
@@ -1034,7 +1049,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.cout_p = L.cout_p;
     a.n_tile = L.n_tile;
     a.n_tiles = L.n_tiles;
-    a.k_blocks = (L.cin_p + kBlockK - 1) / kBlockK;
+    a.k_blocks = (L.cin_p + k_elems - 1) / k_elems;
+    a.k32 = k32 ? 1 : 0;
     a.planes = m->act_planes;
     a.wplanes = m->passes;
     a.out_fp32 = last ? 1 : 0;
@@ -1043,13 +1059,13 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.w_inv_scale = L.w_inv_scale;
     a.acc_cols = round_up(L.n_tile, 32);
     a.half_lp = p->Lp[i] / 2;
-    a.a_tx_bytes = a_box_rows * 128;
+    a.a_tx_bytes = a_box_rows * row_bytes;
     a.pair_magic = ((1ull << 40) / static_cast<unsigned long long>(a.half_lp)) + 1ull;
-    const size_t b_bytes = static_cast<size_t>(L.n_tile) * kBlockK * 2;
+    const size_t b_bytes = static_cast<size_t>(L.n_tile) * row_bytes;
     const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
     const size_t avail = static_cast<size_t>(max_smem) - fixed;
     const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
-    const size_t a_group1 = static_cast<size_t>(m->act_planes) * kATileBytes;
+    const size_t a_group1 = static_cast<size_t>(m->act_planes) * 136 * row_bytes;
     if (allow_resident && L.n_tiles == 1 && w_all + 2 * a_group1 <= avail) {
       // resident weights; as many 128-row sub-tiles per work item as leave >= 2 accumulator
       // stages and >= 2 A groups in flight (amortises the per-item bookkeeping of small-N layers)
@@ -1069,7 +1085,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
         // fused layer 0: A tiles are written by converter warps; one contiguous
         // (ms*128 + 8)-row tile per plane and stage
         for (int ms = want_ms; ms >= 1; ms >>= 1) {
-          const size_t group = static_cast<size_t>(m->act_planes) * (ms * kBlockM + 8) * 128;
+          const size_t group = static_cast<size_t>(m->act_planes) * (ms * kBlockM + 8) * row_bytes;
           if (2 * ms * a.acc_cols <= kTmemCols && w_all + 2 * group <= avail) {
             p->fuse_l0 = 1;
             a.ms = ms;
@@ -1085,8 +1101,11 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     } else {
       a.resident = 0;
       a.ms = (2 * a.acc_cols <= kTmemCols) ? max_ms : 1;
+      if (max_ms == 2 && 4 * a.acc_cols <= kTmemCols && 2 * 4 * a_group1 + 3 * b_bytes <= avail &&
+          env_int("RISER_CONV_MS4_STREAM", 1))
+        a.ms = 4;       // more rows per streamed weight tile (narrow layers / 32-channel K blocks)
       // smem split: at least 2 A groups and 2 B stages; prefer 3+ B stages
-      while (a.ms > 1 && 2 * a.ms * a_group1 + 2 * b_bytes > avail) --a.ms;
+      while (a.ms > 1 && 2 * a.ms * a_group1 + 2 * b_bytes > avail) a.ms >>= 1;
       const size_t a_group = a.ms * a_group1;
       int a_st = 2;
       int b_st = static_cast<int>((avail - a_st * a_group) / b_bytes);
@@ -1119,14 +1138,14 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     }
     RISER_CUDA_TRY(cudaMalloc(&p->flags, p->activity.total));
   }
-  for (int ms = 1; ms <= 4; ms <<= 1)
-    for (int pl = 0; pl < 3; ++pl) {
-      for (int res = (ms == 4 ? 1 : 0); res < 2; ++res)
-        RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, res)),
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, 1, 1)),
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    }
+  for (int k32v = 0; k32v < 2; ++k32v)
+    for (int ms = 1; ms <= 4; ms <<= 1)
+      for (int pl = 0; pl < 3; ++pl)
+        for (int mode = 0; mode < 3; ++mode)     // 0 streamed, 1 resident, 2 resident + fused layer 0
+          RISER_CUDA_TRY(cudaFuncSetAttribute(
+              reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, mode >= 1,
+                                                             mode == 2, k32v)),
+              cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   *out = p;
   return RISER_OK;
 }
@@ -1196,7 +1215,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   a.super0 = static_cast<int>(row0 / rows_per_super);
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
-  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused)<<<grid, fused ? kConvThreads + kCvtThreads : kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32)<<<grid, fused ? kConvThreads + kCvtThreads : kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
