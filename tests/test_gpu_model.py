@@ -25,7 +25,7 @@ CFG = AttrDict({"cnn": {"n_layers": 12, "depth": 1, "channels": synth.CHANNELS, 
                         "n_classes": 2, "classifier": "gap_fc"}})
 # north-star bar: 1e-3 absolute.  X3 (the default) meets it with margin (observed max 1.5e-4,
 # limited by the tensor cores' truncating fp32 accumulation); W2 / F16 are opt-in fast modes.
-PROB_TOL = {PREC_F16_X3: 1e-3, PREC_F16_W2: 2e-3, PREC_F16: 5e-3}   # F16 = opt-in fast mode, outside the 1e-3 bar
+PROB_TOL = {PREC_F16_X3: 1e-3, PREC_F16_W2: 3e-3, PREC_F16: 5e-3}   # F16 = opt-in fast mode, outside the 1e-3 bar
 
 
 def to_device_batch(normed, ld=None):
