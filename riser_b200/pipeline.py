@@ -13,10 +13,26 @@ from . import _lib
 from .preprocess import RaggedBatch, PinnedArena
 from .model import decide, DEFAULT_CHUNK
 
+_EMPTY = np.zeros(0, dtype=np.int16)
+
 # decision codes (include/riser_b200.h)
 TRY_AGAIN, ACCEPT, REJECT, NO_DECISION, SKIPPED = 0, 1, 2, 3, 4
 DECISION_NAMES = {TRY_AGAIN: "try_again", ACCEPT: "accept", REJECT: "reject",
                   NO_DECISION: "no_decision", SKIPPED: "skipped"}
+
+
+def bucket_size(n):
+    """Batch sizes are rounded up to 64, 96, 128, 192, 256, 384, ... (powers of two and 1.5 x powers
+    of two) so that a live run, whose batch size changes every poll, reuses a handful of plans
+    and buffers instead of building new ones; the padding reads have length 0 and cost nothing
+    (their tiles are skipped)."""
+    b = 64
+    while True:
+        if n <= b:
+            return b
+        if n <= b + b // 2:
+            return b + b // 2
+        b *= 2
 
 
 class BatchResult:
@@ -106,7 +122,15 @@ class BatchedClassifier:
             res.sig_len = res.polya_end = np.zeros(0, np.int32)
             res.h2d_bytes = res.d2h_bytes = 0
             return res
-        cached = np.fromiter((polyA_cache.get(r, -1) for r in read_ids), dtype=np.int32, count=B)
+        n_real = B
+        B = bucket_size(n_real)                       # pad with empty reads up to the bucket
+        cached = np.full(B, -1, dtype=np.int32)
+        cached[:n_real] = np.fromiter((polyA_cache.get(r, -1) for r in read_ids), dtype=np.int32, count=n_real)
+        if B > n_real:
+            signals = list(signals) + [_EMPTY] * (B - n_real)
+        # size the staging arena once for the longest prefixes the loop can hand over (a read is
+        # classified, at the latest, once it exceeds fixed trim + max length: control.py:42-46)
+        self._arena.reserve(B * (self.fixed_trim + self.max_len + 8192), B)
         batch = RaggedBatch(signals, self.device, arena=self._arena)
         start, length, detected = self.select_windows(batch, cached)
         decisions, probs = self.run_windows(batch, start, length, threshold, mode)
@@ -120,12 +144,14 @@ class BatchedClassifier:
         host[o2:].copy_(decisions, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         hv = host.numpy()
-        res.sig_len = hv[:o0].view(np.int32).copy()
-        det = hv[o0:o1].view(np.int32).copy()
-        pr = hv[o1:o2].view(np.float32).reshape(M, B, 2)
-        res.decisions = hv[o2:].copy()
+        res.sig_len = hv[:o0].view(np.int32)[:n_real].copy()
+        det = hv[o0:o1].view(np.int32)[:n_real].copy()
+        pr = hv[o1:o2].view(np.float32).reshape(M, B, 2)[:, :n_real]
+        res.decisions = hv[o2:o2 + n_real].copy()
         res.p_off = np.ascontiguousarray(pr[:, :, 0].T)
         res.p_on = np.ascontiguousarray(pr[:, :, 1].T)
+        cached = cached[:n_real]
+        B = n_real
         res.polya_end = np.where(cached >= 0, cached, det)
         res.h2d_bytes = batch.h2d_bytes + cached.nbytes
         res.d2h_bytes = host.numel()
