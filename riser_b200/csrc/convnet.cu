@@ -94,6 +94,7 @@ struct ConvArgs {
   int wplanes;            // weight planes (1, or 2 = hi + lo)
   int out_planes, out_fp32;
   int a_stages, b_stages, acc_stages, resident;
+  int epi_sets;           // epilogue warp sets (each = 4 warps covering the TMEM lane quadrants)
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
@@ -213,13 +214,14 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
 constexpr int kMaxAStages = 8, kMaxBStages = 8, kMaxAccStages = 4;
 constexpr int kConvThreads = 320;
 constexpr int kCvtThreads = 288;         // fused layer 0: converter warps 10..18 (514 rows = 2 passes)
-constexpr int kEpiThreads = 256;
+constexpr int kMaxEpiSets = 4;             // plain kernels: up to four sets (warps 2..17)
 
 struct ConvSmem {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t w_full;
-  uint64_t tmem_full[kMaxAccStages], tmem_empty[kMaxAccStages];
+  uint64_t tmem_full[kMaxAccStages];
+  uint64_t tmem_empty[kMaxAccStages][4];     // per accumulator stage AND sub-tile: released as soon as drained
   uint32_t tmem_base;
   alignas(16) float bias[2][kMaxNTile];
   float4 w0q[32];        // fused layer 0: {w[c][0], w[c][1], w[c][2], bias[c]} per output channel
@@ -326,7 +328,7 @@ struct ItemFlags {
 };
 
 template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false, bool K32 = false>
-__global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : kConvThreads, 1)
+__global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : 64 + 128 * kMaxEpiSets, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
@@ -365,7 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     mbar_init(&s.w_full, 1);
     for (int i = 0; i < a.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], kEpiThreads / 32);
+      for (int ms = 0; ms < MS; ++ms) mbar_init(&s.tmem_empty[i][ms], 4 * a.epi_sets);
     }
     fence_mbar_init();
   }
@@ -446,8 +448,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
         if (!fl.take(cur, item + gridDim.x < n_items)) continue;
-        mbar_wait(&s.tmem_empty[stage], acc_phase ^ 1);
-        tc_fence_after();
         const uint32_t d_base = tmem_base + stage * acc_stride;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
           const int nk = (kb == a.k_blocks - 1) ? nk_last : (kKElems / 16);
@@ -469,6 +469,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const uint64_t db = sw_desc<K32>(b_addr);
 #pragma unroll
               for (int ms = 0; ms < MS; ++ms) {
+                if (kb == 0 && tap == 0 && wp == 0) {   // first touch of this accumulator: wait until drained
+                  mbar_wait(&s.tmem_empty[stage][ms], acc_phase ^ 1);
+                  tc_fence_after();
+                }
 #pragma unroll
                 for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {   // W_lo only meets the hi plane
                   const uint64_t da =
@@ -585,19 +589,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         pa ^= 1;
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + 4 * a.epi_sets) {
     // ===================== epilogue: warps 2..9 = two sets x four lane quadrants =====================
     const int q = warp & 3;
     const int eset = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;        // 0..255
+    const int et = threadIdx.x - 64;        // 0 .. 128 * epi_sets - 1
+    const int epi_threads = 128 * a.epi_sets;
     const bool odd = lane & 1;
     const int row_elems = a.cout_p * a.out_planes;
     const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
     const int n_chunks = a.n_tile >> 4;
     const bool single_n = (a.n_tiles == 1);
     if (single_n) {
-      for (int i = et; i < a.n_tile; i += kEpiThreads) s.bias[0][i] = a.bias[i];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < a.n_tile; i += epi_threads) s.bias[0][i] = a.bias[i];
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
     }
     int stage = 0, it = -1;
     uint32_t acc_phase = 0;
@@ -611,8 +616,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const float* bias_s = s.bias[0];
       if (!single_n) {
         bias_s = s.bias[it & 1];
-        for (int i = et; i < a.n_tile; i += kEpiThreads) s.bias[it & 1][i] = a.bias[n0 + i];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += epi_threads) s.bias[it & 1][i] = a.bias[n0 + i];
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
       }
       // row bookkeeping for every sub-tile (before the accumulator wait, to overlap the loads)
       bool valid[MS], writable[MS];
@@ -640,17 +645,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                          : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
                                 (stage * MS + ms) * a.acc_cols;
-        for (int c = eset; c < n_chunks; c += 2) {
+        for (int c = eset; c < n_chunks; c += a.epi_sets) {
           uint32_t v[16];
           tmem_ld_32x16(t_addr + c * 16, v);
           tmem_ld_wait();
           epilogue_chunk16(v, bias_s, c * 16, odd, valid[ms], writable[ms], orow, a.out_fp32, lo_off,
                            a.w_inv_scale);
         }
+        // this sub-tile's accumulator is drained: the MMA warp may start the next item on it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.tmem_empty[stage][ms]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[stage]);
       if (++stage == a.acc_stages) {
         stage = 0;
         acc_phase ^= 1;
@@ -1118,6 +1124,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fixed + static_cast<size_t>(a.a_stages) * a_group + static_cast<size_t>(a.b_stages) * b_bytes;
     }
     a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+    // four epilogue sets when there are enough 16-column chunks to split (the fused kernel keeps
+    // two: its thread budget goes to the layer-0 converter warps)
+    a.epi_sets = (i == 1 && p->fuse_l0) ? 2 : std::max(2, std::min(env_int("RISER_EPI_SETS", kMaxEpiSets), L.n_tile / 16 >= 4 ? 4 : 2));
     lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
   }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
@@ -1215,7 +1224,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   a.super0 = static_cast<int>(row0 / rows_per_super);
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
-  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32)<<<grid, fused ? kConvThreads + kCvtThreads : kConvThreads, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
