@@ -638,6 +638,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
       mbar_wait(&s.tmem_full[stage], acc_phase);
       tc_fence_after();
+      // work units = (sub-tile, 16-column chunk), dealt round-robin to the epilogue sets
+      int u = eset;
 #pragma unroll
       for (int ms = 0; ms < MS; ++ms) {
         void* orow = a.out_fp32
@@ -645,7 +647,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                          : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) +
                                 (stage * MS + ms) * a.acc_cols;
-        for (int c = eset; c < n_chunks; c += a.epi_sets) {
+        for (; u < (ms + 1) * n_chunks; u += a.epi_sets) {
+          const int c = u - ms * n_chunks;
           uint32_t v[16];
           tmem_ld_32x16(t_addr + c * 16, v);
           tmem_ld_wait();
@@ -1126,7 +1129,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
     // four epilogue sets when there are enough 16-column chunks to split (the fused kernel keeps
     // two: its thread budget goes to the layer-0 converter warps)
-    a.epi_sets = (i == 1 && p->fuse_l0) ? 2 : std::max(2, std::min(env_int("RISER_EPI_SETS", kMaxEpiSets), L.n_tile / 16 >= 4 ? 4 : 2));
+    a.epi_sets = (i == 1 && p->fuse_l0) ? 2 : std::max(2, std::min(env_int("RISER_EPI_SETS", kMaxEpiSets), 4));
     lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
   }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
