@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libriser_b200.so")
+LIB_PATH = os.environ.get("RISER_B200_LIB", os.path.join(HERE, "libriser_b200.so"))
 
 c_int, c_i64, c_void_p, c_size_t, c_float = (ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_size_t, ctypes.c_float)
