@@ -122,6 +122,7 @@ struct LayerPlan {
   CUtensorMap tm_a, tm_b;
   ConvArgs args;
   int n_supers_total = 0;
+  int rows_per_super = 0;   // flat input rows one work item covers (ms * 128; 510 for the fused layers 0+1)
   int flag_off = 0;
   size_t smem = 0;
 };
@@ -132,7 +133,8 @@ struct LayerPlan {
 struct riser_plan {
   const riser_model* model = nullptr;
   int B = 0, max_len = 0;
-  int fuse_l0 = 0;                      // layer 0 computed inside layer 1's kernel
+  int fuse_l0 = 0;                      // layer 0 computed inside layer 1's launch: 1 = CUDA-core converter warps
+                                        // (conv_tc_kernel<FUSED>), 2 = both layers on the tensor pipe (fused01_kernel)
   uint8_t* flags = nullptr;             // tile activity flags (plan-owned), see tile_activity_kernel
   riser::ActivityArgs activity;
   int chunk_reads = 0, n_chunked = 0;   // early layers 0..n_chunked-1 run chunk by chunk (L2 residency)
@@ -526,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
       if (!fl.take(cur, item + gridDim.x < n_items)) continue;
       const int r0 = cur.super * (MS * kBlockM) - 1;
-      mbar_wait(&s.a_empty[sa], pa ^ 1);
+      mbar_wait_relaxed(&s.a_empty[sa], pa ^ 1);
       unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroupBytes;
       for (int j = ct; j < kRows; j += kCvtThreads) {
         const int r = r0 + j;
@@ -636,7 +638,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           out_row[ms] = static_cast<int64_t>(b) * a.Lp_out + tp;
         }
       }
-      mbar_wait(&s.tmem_full[stage], acc_phase);
+      mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
       tc_fence_after();
       // work units = (sub-tile, 16-column chunk), dealt round-robin to the epilogue sets
       int u = eset;
@@ -702,6 +704,440 @@ ConvKernelFn pick_conv_k(int ms, int planes, int wplanes, int resident, int fuse
 ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0, int k32 = 0) {
   return k32 ? pick_conv_k<true>(ms, planes, wplanes, resident, fused)
              : pick_conv_k<false>(ms, planes, wplanes, resident, fused);
+}
+
+// ------------------------------------------------------------------------------------
+// Layers 0 + 1 in one launch, BOTH on the tensor pipe (RISER_FUSE_L0=2, the default).
+//
+// Layer 0 (Conv1d(1->C0,k3,same)+ReLU+MaxPool, nets/cnn.py:55-64) is a GEMM with K = 16:
+// row p of its A operand is the signal window x[2p-1 .. 2p+2] split into fp16 hi and lo
+// parts plus a constant-one column, and its B operand holds, for the conv position 2p
+// (columns 0..23) and 2p+1 (columns 24..47), the taps as fp16 hi + lo and the bias:
+//     k:  0..3  x_hi  * w_hi      4..7  x_lo * w_hi      8..11  x_hi * w_lo      12,13  1 * (b_hi, b_lo)
+// (everything but the 2^-22 x_lo*w_lo term of the fp32 product).  The two positions of a
+// max-pool pair therefore sit in ONE accumulator row (TMEM lane): pooling is an in-lane max.
+//
+// The same trick is applied to layer 1: its input rows are kept in shared memory as an
+// "E" tile (even rows 2j) and an "O" tile (odd rows 2j+1), so that the conv at position 2j
+//     w0*O[j-1] + w1*E[j] + w2*O[j]          and at 2j+1      w0*E[j] + w1*O[j] + w2*E[j+1]
+// are row-shifted views of the two tiles accumulated into two column ranges of the same lane.
+//
+// Work item = 255 pooled layer-1 outputs (pair indices u0 .. u0+254; E rows 0..255 = E[u0+i],
+// O rows 0..255 = O[u0+i-1]).  Roles (20 warps):
+//   warps 0,2,3   cvt1: normalised signal -> layer-0 A rows in shared memory
+//   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
+//   warps 4..11   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
+//   warps 12..19  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
+constexpr int kF2Pairs = 255;
+constexpr int kF2Threads = 640;
+constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shifted taps of row 255 touch
+constexpr uint32_t kF2A0Tile = 256 * 64;   // per row: [E window (K=16) | O window (K=16)]
+constexpr int kF2N0 = 48;
+constexpr int kF2D0Col = 256;              // TMEM: layer-1 accumulators [0,256), layer-0 at 256 + 48*k
+constexpr int kF2CvtThreads = 96;
+
+struct F2Smem {
+  uint64_t w_full;
+  uint64_t a0_full[2], a0_empty[2];
+  uint64_t d0_full[2], d0_empty[2];          // halves: 0 = E sub-tiles, 1 = O sub-tiles
+  uint64_t a1_full[2], a1_empty[2];
+  uint64_t d1_full[2], d1_empty[2][2];
+  uint32_t tmem_base;
+  alignas(16) float bias[32];
+};
+
+// Active work items of this CTA in order; the next item's flag is loaded one item ahead.
+struct F2Iter {
+  const uint8_t* flags;
+  int item, n_items, step;
+  uint32_t f_next;
+  __device__ __forceinline__ F2Iter(const uint8_t* f, int n) : flags(f), item(blockIdx.x), n_items(n), step(gridDim.x) {
+    f_next = (flags && item < n_items) ? __ldg(flags + item) : 1u;
+  }
+  __device__ __forceinline__ int take() {
+    while (item < n_items) {
+      const int cur = item;
+      const uint32_t f = f_next;
+      item += step;
+      f_next = (flags && item < n_items) ? __ldg(flags + item) : 1u;
+      if (f) return cur;
+    }
+    return -1;
+  }
+};
+
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+template <int PLANES, int WPLANES>
+__global__ void __launch_bounds__(kF2Threads, 1)
+fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  constexpr uint32_t kW1Bytes = WPLANES * 3 * 32 * 64;
+  constexpr uint32_t kB0Bytes = kF2N0 * 64;
+  constexpr uint32_t kA1Stage = PLANES * 2 * kF2A1Tile;
+  unsigned char* w1 = base;
+  unsigned char* b0 = w1 + kW1Bytes;
+  unsigned char* a0_ring = b0 + kB0Bytes;                 // 2 stages
+  unsigned char* a1_ring = a0_ring + 2 * kF2A0Tile;       // 2 stages x [plane][E, O]
+  F2Smem& s = *reinterpret_cast<F2Smem*>(a1_ring + 2 * kA1Stage);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_items = a.n_supers;
+  const int n_pairs = a.rows_in >> 1;
+  const uint8_t* flags0 = a.flags ? a.flags + a.super0 : nullptr;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_b);
+    mbar_init(&s.w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.a0_full[i], 3);
+      mbar_init(&s.a0_empty[i], 1);
+      mbar_init(&s.d0_full[i], 1);
+      mbar_init(&s.d0_empty[i], 4);
+      mbar_init(&s.a1_full[i], 8);
+      mbar_init(&s.a1_empty[i], 1);
+      mbar_init(&s.d1_full[i], 1);
+      mbar_init(&s.d1_empty[i][0], 4);
+      mbar_init(&s.d1_empty[i][1], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s.tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  // zero both operand rings once: padded channels / unused K columns are never written again
+  for (uint32_t i = threadIdx.x; i < (2 * kF2A0Tile + 2 * kA1Stage) / 16; i += kF2Threads)
+    reinterpret_cast<uint4*>(a0_ring)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 32) s.bias[threadIdx.x] = a.bias[threadIdx.x];
+  if (threadIdx.x < kF2N0) {
+    // layer-0 B operand, row n: channel n % 24 at conv position 2p + n / 24 (SWIZZLE_64B rows)
+    const int n = threadIdx.x, c = n % 24, odd = n / 24;
+    float w[3] = {0.f, 0.f, 0.f}, bb = 0.f;
+    if (c < a.cout0) {
+      w[0] = a.w0[c * 3];
+      w[1] = a.w0[c * 3 + 1];
+      w[2] = a.w0[c * 3 + 2];
+      bb = a.b0[c];
+    }
+    __half kh[4], kl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) kh[k] = kl[k] = __float2half_rn(0.f);
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const __half h = __float2half_rn(w[tap]);
+      kh[tap + odd] = h;
+      kl[tap + odd] = __float2half_rn(w[tap] - __half2float(h));
+    }
+    const __half bh = __float2half_rn(bb), bl = __float2half_rn(bb - __half2float(bh));
+    __half c0[8] = {kh[0], kh[1], kh[2], kh[3], kh[0], kh[1], kh[2], kh[3]};
+    __half c1[8] = {kl[0], kl[1], kl[2], kl[3], bh, bl, __float2half_rn(0.f), __float2half_rn(0.f)};
+    const int sw = (n >> 1) & 3;
+    *reinterpret_cast<uint4*>(b0 + n * 64 + ((0 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(c0);
+    *reinterpret_cast<uint4*>(b0 + n * 64 + ((1 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(c1);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0 && lane == 0) {     // layer-1 weights: resident for the whole kernel
+    mbar_arrive_expect_tx(&s.w_full, kW1Bytes);
+    for (int wp = 0; wp < WPLANES; ++wp)
+      for (int tap = 0; tap < 3; ++tap)
+        tma_load_2d(w1 + (wp * 3 + tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+  }
+  __syncwarp();
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(&s.w_full, 0);
+      tc_fence_after();
+      const uint32_t w1_addr = smem_u32(w1), b0_addr = smem_u32(b0);
+      const uint32_t a0_addr = smem_u32(a0_ring), a1_addr = smem_u32(a1_ring);
+      const uint32_t idesc0 = umma_idesc_f16(kBlockM, kF2N0);
+      const uint64_t db0 = sw_desc<true>(b0_addr);
+      F2Iter iter(flags0, n_items);
+      int k0 = 0;                       // items whose layer 0 has been issued
+      auto issue_layer0 = [&]() {
+        const int st = k0 & 1;
+        mbar_wait(&s.a0_full[st], (k0 >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&s.d0_empty[h], (k0 & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+            umma_f16(tmem_base + kF2D0Col + (h * 2 + sub) * kF2N0,
+                     sw_desc<true>(a0_addr + st * kF2A0Tile + sub * 128 * 64) + 2 * h, db0, idesc0, 0);
+          umma_commit(&s.d0_full[h]);
+        }
+        umma_commit(&s.a0_empty[st]);
+        ++k0;
+      };
+      int cur = iter.take();
+      if (cur >= 0) issue_layer0();
+      int k1 = 0;                       // items whose layer 1 has been issued
+      while (cur >= 0) {
+        const int nxt = iter.take();
+        if (nxt >= 0) issue_layer0();
+        const int st = k1 & 1;
+        mbar_wait(&s.a1_full[st], (k1 >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a1s = a1_addr + st * kA1Stage;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          mbar_wait(&s.d1_empty[st][sub], ((k1 >> 1) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int pe = 0; pe < 2; ++pe) {
+            const uint32_t d = tmem_base + st * 128 + (2 * sub + pe) * 32;
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) {
+              // even position: O[j-1], E[j], O[j];  odd position: E[j], O[j], E[j+1]
+              const int par = (pe == 0) ? ((tap == 1) ? 0 : 1) : ((tap == 1) ? 1 : 0);
+              const int shift = (pe == 0) ? ((tap == 2) ? 1 : 0) : ((tap == 0) ? 0 : 1);
+#pragma unroll
+              for (int wp = 0; wp < WPLANES; ++wp) {
+                const uint64_t db = sw_desc<true>(w1_addr + (wp * 3 + tap) * 2048);
+#pragma unroll
+                for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {
+                  const uint64_t da =
+                      sw_desc<true>(a1s + (ap * 2 + par) * kF2A1Tile + (sub * 128 + shift) * 64);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+                    umma_f16(d, da + 2 * k, db + 2 * k, a.idesc, (tap | wp | ap | k) != 0);
+                }
+              }
+            }
+          }
+        }
+        umma_commit(&s.a1_empty[st]);
+        umma_commit(&s.d1_full[st]);
+        ++k1;
+        cur = nxt;
+      }
+    }
+  } else if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== cvt1: signal -> layer-0 A rows =====================
+    const int ct = (warp == 0 ? 0 : warp - 1) * 32 + lane;      // 0..95
+    const __half2 one2 = __floats2half2_rn(1.f, 1.f);
+    F2Iter iter(flags0, n_items);
+    int k = 0;
+    for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
+      const int st = k & 1;
+      mbar_wait_relaxed(&s.a0_empty[st], ((k >> 1) & 1) ^ 1);
+      unsigned char* tile = a0_ring + st * kF2A0Tile;
+      const long long u0 = static_cast<long long>(a.super0 + item) * kF2Pairs;
+      for (int i = ct - 1; i <= 255; i += kF2CvtThreads) {
+        const long long u = u0 + i;
+        const bool inb = (u >= 0 && u < n_pairs);
+        const uint32_t uu = inb ? static_cast<uint32_t>(u) : 0u;
+        const int b = static_cast<int>((static_cast<unsigned long long>(uu) * a.pair_magic) >> 40);
+        const int t4 = 4 * (static_cast<int>(uu) - b * a.half_lp);
+        const float* xr = a.x + static_cast<long long>(b) * a.ld_x + t4;
+        const int L = inb ? __ldg(a.len0 + b) : 0;
+        const bool ld0 = inb && (t4 + 1 < a.ld_x), ld2 = inb && (t4 + 3 < a.ld_x);
+        const float2 x01 = ld0 ? __ldg(reinterpret_cast<const float2*>(xr)) : make_float2(0.f, 0.f);
+        const float2 x23 = ld2 ? __ldg(reinterpret_cast<const float2*>(xr + 2)) : make_float2(0.f, 0.f);
+        float xm1 = (ld0 && t4 > 0) ? __ldg(xr - 1) : 0.f;
+        float x4 = (inb && t4 + 4 < a.ld_x) ? __ldg(xr + 4) : 0.f;
+        const int half_len = L >> 1;
+        const bool e_ok = (t4 >> 1) < half_len;          // row p = 2t is a valid pooled layer-0 row
+        const bool o_ok = (t4 >> 1) + 1 < half_len;      // row p = 2t + 1
+        float x2 = (t4 + 2 < L) ? x23.x : 0.f;           // 'same' padding at the end of the read
+        if (t4 + 4 >= L) x4 = 0.f;
+        // fp16 range guard (|x| > 65504 only for pathological reads; the old path saturated too)
+        auto clampf = [](float v) { return fminf(fmaxf(v, -65504.f), 65504.f); };
+        const float v[6] = {clampf(xm1), clampf(x01.x), clampf(x01.y), clampf(x2), clampf(x23.y), clampf(x4)};
+        __half2 hi[3], lo[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          hi[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          const float2 back = __half22float2(hi[j]);
+          lo[j] = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+        }
+        // windows: E = v[0..3]; O = v[2..5]
+        if (i >= 0) {
+          unsigned char* row = tile + i * 64;
+          const int sw = (i >> 1) & 3;
+          uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
+          if (e_ok) {
+            c0 = make_uint4(h2_bits(hi[0]), h2_bits(hi[1]), h2_bits(lo[0]), h2_bits(lo[1]));
+            c1 = make_uint4(h2_bits(hi[0]), h2_bits(hi[1]), h2_bits(one2), 0u);
+          }
+          *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = c0;
+          *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = c1;
+        }
+        if (i + 1 <= 255) {
+          unsigned char* row = tile + (i + 1) * 64;
+          const int sw = ((i + 1) >> 1) & 3;
+          uint4 c2 = make_uint4(0, 0, 0, 0), c3 = make_uint4(0, 0, 0, 0);
+          if (o_ok) {
+            c2 = make_uint4(h2_bits(hi[1]), h2_bits(hi[2]), h2_bits(lo[1]), h2_bits(lo[2]));
+            c3 = make_uint4(h2_bits(hi[1]), h2_bits(hi[2]), h2_bits(one2), 0u);
+          }
+          *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = c2;
+          *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = c3;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.a0_full[st]);
+    }
+  } else if (warp < 12) {
+    // ===================== mid-epilogue: layer-0 accumulators -> layer-1 A tiles =====================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;                      // 0: E sub-tiles, 1: O sub-tiles
+    F2Iter iter(flags0, n_items);
+    int k = 0;
+    for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
+      const int st = k & 1;
+      mbar_wait_relaxed(&s.a1_empty[st], ((k >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&s.d0_full[h], k & 1);
+      tc_fence_after();
+      unsigned char* tile_hi = a1_ring + st * kA1Stage + h * kF2A1Tile;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + kF2D0Col + (h * 2 + sub) * kF2N0;
+        uint32_t e0[16], e1[8], o0[16], o1[8];
+        tmem_ld_32x16(taddr, e0);
+        tmem_ld_32x8(taddr + 16, e1);
+        tmem_ld_32x16(taddr + 24, o0);
+        tmem_ld_32x8(taddr + 40, o1);
+        tmem_ld_wait();
+        if (sub == 1) {          // both sub-tiles are in registers: layer 0 of the next item may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.d0_empty[h]);
+        }
+        const int row = sub * 128 + 32 * q + lane;
+        unsigned char* rp = tile_hi + row * 64;
+        const int sw = (row >> 1) & 3;
+#pragma unroll
+        for (int c8 = 0; c8 < 3; ++c8) {
+          __half2 hv[4], lv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = c8 * 8 + 2 * j + e;
+              const float ev = __uint_as_float(c < 16 ? e0[c & 15] : e1[c & 7]);
+              const float ov = __uint_as_float(c < 16 ? o0[c & 15] : o1[c & 7]);
+              v[e] = fmaxf(fmaxf(ev, ov), 0.f);
+            }
+            hv[j] = sat_half2(v[0], v[1]);
+            if (PLANES == 2) {
+              const float2 back = __half22float2(hv[j]);
+              lv[j] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+            }
+          }
+          const int off = (c8 ^ sw) << 4;
+          *reinterpret_cast<uint4*>(rp + off) = *reinterpret_cast<const uint4*>(hv);
+          if (PLANES == 2) *reinterpret_cast<uint4*>(rp + 2 * kF2A1Tile + off) = *reinterpret_cast<const uint4*>(lv);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.a1_full[st]);
+    }
+  } else {
+    // ===================== epilogue: layer-1 accumulators -> act_2 =====================
+    const int q = warp & 3;
+    const int sub = (warp - 12) >> 2;
+    const int row_elems = a.cout_p * a.out_planes;
+    const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
+    const float inv_scale = a.w_inv_scale;
+    F2Iter iter(flags0, n_items);
+    int k = 0;
+    for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
+      const int st = k & 1;
+      const int j = sub * 128 + 32 * q + lane;
+      const long long u = static_cast<long long>(a.super0 + item) * kF2Pairs + j;
+      const bool ok = (j < kF2Pairs) && (u < n_pairs);
+      const uint32_t uu = ok ? static_cast<uint32_t>(u) : 0u;
+      const int b = static_cast<int>((static_cast<unsigned long long>(uu) * a.pair_magic) >> 40);
+      const int tp = static_cast<int>(uu) - b * a.half_lp;
+      const bool valid = ok && tp < (__ldg(a.len0 + b) >> a.shift);
+      const bool writable = ok && tp < a.Lp_out;
+      __half* orow = static_cast<__half*>(a.out) + (static_cast<int64_t>(b) * a.Lp_out + tp) * row_elems;
+      mbar_wait_relaxed(&s.d1_full[st], (k >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + st * 128 + 2 * sub * 32;
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        uint32_t ve[16], vo[16];
+        tmem_ld_32x16(taddr + c16 * 16, ve);
+        tmem_ld_32x16(taddr + 32 + c16 * 16, vo);
+        tmem_ld_wait();
+        if (c16 == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.d1_empty[st][sub]);
+        }
+        if (writable) {
+          float r[16];
+          if (valid) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&s.bias[c16 * 16 + c4 * 4]);
+              const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = c4 * 4 + e;
+                r[c] = fmaxf(fmaf(fmaxf(__uint_as_float(ve[c]), __uint_as_float(vo[c])), inv_scale, bv[e]), 0.f);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) r[c] = 0.f;
+          }
+          __half2 hv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
+          uint4* oh = reinterpret_cast<uint4*>(orow + c16 * 16);
+          oh[0] = *reinterpret_cast<const uint4*>(hv);
+          oh[1] = *reinterpret_cast<const uint4*>(hv + 4);
+          if (lo_off) {
+            __half2 lv[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float2 back = __half22float2(hv[c]);
+              lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
+            }
+            uint4* ol = reinterpret_cast<uint4*>(orow + lo_off + c16 * 16);
+            ol[0] = *reinterpret_cast<const uint4*>(lv);
+            ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*FusedKernelFn)(const CUtensorMap, const ConvArgs);
+FusedKernelFn pick_fused01(int planes, int wplanes) {
+  if (planes == 1 && wplanes == 1) return fused01_kernel<1, 1>;
+  if (planes == 1 && wplanes == 2) return fused01_kernel<1, 2>;
+  return fused01_kernel<2, 2>;
+}
+size_t fused01_smem(int planes, int wplanes) {
+  return 1024 + static_cast<size_t>(wplanes) * 3 * 32 * 64 + kF2N0 * 64 + 2 * kF2A0Tile +
+         2 * static_cast<size_t>(planes) * 2 * kF2A1Tile + sizeof(F2Smem) + 64;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1036,7 +1472,10 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const int a_box_rows = env_int("RISER_A_BOX_ROWS", 136);   // 130 needed; a multiple of 8 is what TMA likes
     // 32-channel K blocks (64-byte rows, SWIZZLE_64B) for narrow layers: no zero-filled half rows,
     // twice the pipeline depth / sub-tiles per item in the same shared memory
-    const bool k32 = L.cin_p <= env_int("RISER_K32_MAX_CIN", 80);
+    const int want_fuse = env_int("RISER_FUSE_L0", 2);
+    const bool fuse2 = (i == 1 && want_fuse == 2 && L.cin_p == 32 && L.n_tile == 32 && L.n_tiles == 1 &&
+                        m->layer[0].cout <= 24);
+    const bool k32 = fuse2 || L.cin_p <= env_int("RISER_K32_MAX_CIN", 80);
     const int row_bytes = k32 ? 64 : 128;
     const int k_elems = row_bytes / 2;
     int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
@@ -1090,7 +1529,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b_stages = 1;
       a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / (a.ms * a_group1)));
       lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * a.ms * a_group1;
-      if (i == 1 && L.cin_p == 32 && env_int("RISER_FUSE_L0", 1)) {
+      if (i == 1 && L.cin_p == 32 && want_fuse == 1) {
         // fused layer 0: A tiles are written by converter warps; one contiguous
         // (ms*128 + 8)-row tile per plane and stage
         for (int ms = want_ms; ms >= 1; ms >>= 1) {
@@ -1130,7 +1569,17 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     // four epilogue sets when there are enough 16-column chunks to split (the fused kernel keeps
     // two: its thread budget goes to the layer-0 converter warps)
     a.epi_sets = (i == 1 && p->fuse_l0) ? 2 : std::max(2, std::min(env_int("RISER_EPI_SETS", kMaxEpiSets), 4));
-    lp.n_supers_total = (rows_in + a.ms * kBlockM - 1) / (a.ms * kBlockM);
+    lp.rows_per_super = a.ms * kBlockM;
+    if (fuse2) {
+      // layers 0 + 1 on the tensor pipe (fused01_kernel): work item = 255 pooled outputs = 510 input rows
+      p->fuse_l0 = 2;
+      a.w0 = m->layer[0].w0;
+      a.b0 = m->layer[0].bias;
+      a.cout0 = m->layer[0].cout;
+      lp.rows_per_super = 2 * kF2Pairs;
+      lp.smem = fused01_smem(m->act_planes, m->passes);
+    }
+    lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
   }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
   p->activity.n_layers = 0;
@@ -1141,7 +1590,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       ActivityLayer& al = p->activity.layer[p->activity.n_layers++];
       al.Lp_in = a.Lp_in;
       al.rows_in = a.rows_in;
-      al.rows_per_super = a.ms * kBlockM;
+      al.rows_per_super = p->layer[i].rows_per_super;
       al.shift = a.shift;
       al.n_supers = p->layer[i].n_supers_total;
       al.flag_off = p->activity.total;
@@ -1158,6 +1607,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
               reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, mode >= 1,
                                                              mode == 2, k32v)),
               cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  for (int pl = 0; pl < 3; ++pl)
+    RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl == 2 ? 2 : 1, pl == 0 ? 1 : 2)),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   *out = p;
   return RISER_OK;
 }
@@ -1215,18 +1667,24 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   const LayerPlan& lp = p->layer[i];
   ConvArgs a = lp.args;
   a.len0 = len;
-  const int fused = (i == 1 && p->fuse_l0) ? 1 : 0;
+  const int fused = (i == 1 && p->fuse_l0 == 1) ? 1 : 0;
+  const bool fused2 = (i == 1 && p->fuse_l0 == 2);
   a.flags = p->flags ? p->flags + lp.flag_off : nullptr;
-  if (fused) {
+  if (fused || fused2) {
     RISER_REQUIRE(x, "riser_forward: null x");
     a.x = x;
     a.ld_x = ld_x;
   }
-  const int64_t rows_per_super = static_cast<int64_t>(a.ms) * kBlockM;
+  const int64_t rows_per_super = lp.rows_per_super;
   const int64_t row0 = static_cast<int64_t>(b0) * a.Lp_in, row1 = static_cast<int64_t>(b0 + nb) * a.Lp_in;
   a.super0 = static_cast<int>(row0 / rows_per_super);
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
+  if (fused2) {
+    pick_fused01(a.planes, a.wplanes)<<<grid, kF2Threads, lp.smem, st>>>(lp.tm_b, a);
+    RISER_CUDA_TRY(cudaGetLastError());
+    return RISER_OK;
+  }
   pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;

@@ -49,7 +49,8 @@ def oracle_layers(state, x):
 
 
 @pytest.mark.parametrize("fuse,precision", [(0, PREC_F16), (0, PREC_F16_W2), (0, PREC_F16_X3), (1, PREC_F16),
-                                            (1, PREC_F16_W2), (1, PREC_F16_X3)])
+                                            (1, PREC_F16_W2), (1, PREC_F16_X3), (2, PREC_F16), (2, PREC_F16_W2),
+                                            (2, PREC_F16_X3)])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
     rng = np.random.default_rng(0)
