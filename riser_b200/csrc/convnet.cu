@@ -724,7 +724,8 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
 //
 // Work item = 255 pooled layer-1 outputs (pair indices u0 .. u0+254; E rows 0..255 = E[u0+i],
 // O rows 0..255 = O[u0+i-1]).  Roles (20 warps):
-//   warps 0,2,3   cvt1: normalised signal -> layer-0 A rows in shared memory
+//   warp 0        producer: bulk copies (TMA) of the item's signal segment into a 4-stage ring
+//   warps 2,3     cvt1: signal (shared memory) -> layer-0 A rows in shared memory
 //   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
 //   warps 4..11   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
 //   warps 12..19  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
@@ -734,10 +735,13 @@ constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shift
 constexpr uint32_t kF2A0Tile = 256 * 64;   // per row: [E window (K=16) | O window (K=16)]
 constexpr int kF2N0 = 48;
 constexpr int kF2D0Col = 256;              // TMEM: layer-1 accumulators [0,256), layer-0 at 256 + 48*k
-constexpr int kF2CvtThreads = 96;
+constexpr int kF2CvtThreads = 64;
+constexpr int kF2XStages = 4;
+constexpr uint32_t kF2XStage = 260 * 16;     // pairs i = -2 .. 256 (4 samples each) + pad
 
 struct F2Smem {
   uint64_t w_full;
+  uint64_t x_full[kF2XStages], x_empty[kF2XStages];
   uint64_t a0_full[2], a0_empty[2];
   uint64_t d0_full[2], d0_empty[2];          // halves: 0 = E sub-tiles, 1 = O sub-tiles
   uint64_t a1_full[2], a1_empty[2];
@@ -780,7 +784,8 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
   unsigned char* b0 = w1 + kW1Bytes;
   unsigned char* a0_ring = b0 + kB0Bytes;                 // 2 stages
   unsigned char* a1_ring = a0_ring + 2 * kF2A0Tile;       // 2 stages x [plane][E, O]
-  F2Smem& s = *reinterpret_cast<F2Smem*>(a1_ring + 2 * kA1Stage);
+  unsigned char* x_ring = a1_ring + 2 * kA1Stage;         // signal segments, kF2XStages stages
+  F2Smem& s = *reinterpret_cast<F2Smem*>(x_ring + kF2XStages * kF2XStage);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -791,8 +796,12 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_b);
     mbar_init(&s.w_full, 1);
+    for (int i = 0; i < kF2XStages; ++i) {
+      mbar_init(&s.x_full[i], 1);
+      mbar_init(&s.x_empty[i], 2);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.a0_full[i], 3);
+      mbar_init(&s.a0_full[i], 2);
       mbar_init(&s.a0_empty[i], 1);
       mbar_init(&s.d0_full[i], 1);
       mbar_init(&s.d0_empty[i], 4);
@@ -809,7 +818,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
     tmem_relinquish();
   }
   // zero both operand rings once: padded channels / unused K columns are never written again
-  for (uint32_t i = threadIdx.x; i < (2 * kF2A0Tile + 2 * kA1Stage) / 16; i += kF2Threads)
+  for (uint32_t i = threadIdx.x; i < (2 * kF2A0Tile + 2 * kA1Stage + kF2XStages * kF2XStage) / 16; i += kF2Threads)
     reinterpret_cast<uint4*>(a0_ring)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 32) s.bias[threadIdx.x] = a.bias[threadIdx.x];
   if (threadIdx.x < kF2N0) {
@@ -844,15 +853,51 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
-  if (warp == 0 && lane == 0) {     // layer-1 weights: resident for the whole kernel
-    mbar_arrive_expect_tx(&s.w_full, kW1Bytes);
-    for (int wp = 0; wp < WPLANES; ++wp)
-      for (int tap = 0; tap < 3; ++tap)
-        tma_load_2d(w1 + (wp * 3 + tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
-  }
-  __syncwarp();
-
-  if (warp == 1) {
+  if (warp == 0) {
+    // ===================== producer: weights once, then the signal segment of every item =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&s.w_full, kW1Bytes);
+      for (int wp = 0; wp < WPLANES; ++wp)
+        for (int tap = 0; tap < 3; ++tap)
+          tma_load_2d(w1 + (wp * 3 + tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+      // Stage slot of pair i (i = -2 .. 256) is 16*(i+2): its four samples x[4t .. 4t+3].  An item spans at
+      // most two reads (a read has more pairs than an item); pairs with 4t >= ld_x are not loaded (they lie
+      // beyond every valid length and are masked by cvt1).
+      const int t_max = static_cast<int>(a.ld_x >> 2);        // pairs per read that exist in x
+      F2Iter iter(flags0, n_items);
+      int k = 0;
+      for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
+        const int st = k % kF2XStages;
+        mbar_wait(&s.x_empty[st], ((k / kF2XStages) & 1) ^ 1);
+        unsigned char* dst = x_ring + st * kF2XStage;
+        long long u_lo = static_cast<long long>(a.super0 + item) * kF2Pairs - 2;
+        long long u_hi = u_lo + 258;                            // inclusive
+        const int i_lo = (u_lo < 0) ? static_cast<int>(-u_lo) - 2 : -2;
+        if (u_lo < 0) u_lo = 0;
+        if (u_hi > n_pairs - 1) u_hi = n_pairs - 1;
+        uint32_t bytes[2] = {0, 0};
+        const float* src[2] = {nullptr, nullptr};
+        int slot[2] = {0, 0};
+        if (u_hi >= u_lo) {
+          const int b = static_cast<int>((static_cast<unsigned long long>(static_cast<uint32_t>(u_lo)) * a.pair_magic) >> 40);
+          const int t0 = static_cast<int>(u_lo) - b * a.half_lp;
+          const int n_total = static_cast<int>(u_hi - u_lo) + 1;
+          const int n_first = min(n_total, a.half_lp - t0);     // pairs that belong to read b
+          const int n1 = max(0, min(n_first, t_max - t0));
+          src[0] = a.x + static_cast<long long>(b) * a.ld_x + 4 * t0;
+          slot[0] = i_lo + 2;
+          bytes[0] = 16u * n1;
+          const int n2 = max(0, min(n_total - n_first, t_max));
+          src[1] = a.x + static_cast<long long>(b + 1) * a.ld_x;
+          slot[1] = i_lo + 2 + n_first;
+          bytes[1] = 16u * n2;
+        }
+        mbar_arrive_expect_tx(&s.x_full[st], bytes[0] + bytes[1]);
+        if (bytes[0]) bulk_load_1d(dst + 16 * slot[0], src[0], bytes[0], &s.x_full[st]);
+        if (bytes[1]) bulk_load_1d(dst + 16 * slot[1], src[1], bytes[1], &s.x_full[st]);
+      }
+    }
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_wait(&s.w_full, 0);
@@ -923,16 +968,19 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
         cur = nxt;
       }
     }
-  } else if (warp == 0 || warp == 2 || warp == 3) {
+  } else if (warp < 4) {
     // ===================== cvt1: signal -> layer-0 A rows =====================
-    const int ct = (warp == 0 ? 0 : warp - 1) * 32 + lane;      // 0..95
+    const int ct = (warp - 2) * 32 + lane;      // 0..63
     const __half2 one2 = __floats2half2_rn(1.f, 1.f);
     F2Iter iter(flags0, n_items);
     int k = 0;
     for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
       const int st = k & 1;
+      const int xst = k % kF2XStages;
+      mbar_wait_relaxed(&s.x_full[xst], (k / kF2XStages) & 1);
       mbar_wait_relaxed(&s.a0_empty[st], ((k >> 1) & 1) ^ 1);
       unsigned char* tile = a0_ring + st * kF2A0Tile;
+      const float* xs = reinterpret_cast<const float*>(x_ring + xst * kF2XStage) + 8;   // xs[4*i + e]
       const long long u0 = static_cast<long long>(a.super0 + item) * kF2Pairs;
       for (int i = ct - 1; i <= 255; i += kF2CvtThreads) {
         const long long u = u0 + i;
@@ -940,13 +988,11 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
         const uint32_t uu = inb ? static_cast<uint32_t>(u) : 0u;
         const int b = static_cast<int>((static_cast<unsigned long long>(uu) * a.pair_magic) >> 40);
         const int t4 = 4 * (static_cast<int>(uu) - b * a.half_lp);
-        const float* xr = a.x + static_cast<long long>(b) * a.ld_x + t4;
         const int L = inb ? __ldg(a.len0 + b) : 0;
-        const bool ld0 = inb && (t4 + 1 < a.ld_x), ld2 = inb && (t4 + 3 < a.ld_x);
-        const float2 x01 = ld0 ? __ldg(reinterpret_cast<const float2*>(xr)) : make_float2(0.f, 0.f);
-        const float2 x23 = ld2 ? __ldg(reinterpret_cast<const float2*>(xr + 2)) : make_float2(0.f, 0.f);
-        float xm1 = (ld0 && t4 > 0) ? __ldg(xr - 1) : 0.f;
-        float x4 = (inb && t4 + 4 < a.ld_x) ? __ldg(xr + 4) : 0.f;
+        const float4 x03 = *reinterpret_cast<const float4*>(xs + 4 * i);
+        const float2 x01 = make_float2(x03.x, x03.y), x23 = make_float2(x03.z, x03.w);
+        float xm1 = (t4 > 0) ? xs[4 * i - 1] : 0.f;
+        float x4 = xs[4 * i + 4];
         const int half_len = L >> 1;
         const bool e_ok = (t4 >> 1) < half_len;          // row p = 2t is a valid pooled layer-0 row
         const bool o_ok = (t4 >> 1) + 1 < half_len;      // row p = 2t + 1
@@ -988,7 +1034,10 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.a0_full[st]);
+      if (lane == 0) {
+        mbar_arrive(&s.x_empty[xst]);
+        mbar_arrive(&s.a0_full[st]);
+      }
     }
   } else if (warp < 12) {
     // ===================== mid-epilogue: layer-0 accumulators -> layer-1 A tiles =====================
@@ -1137,7 +1186,7 @@ FusedKernelFn pick_fused01(int planes, int wplanes) {
 }
 size_t fused01_smem(int planes, int wplanes) {
   return 1024 + static_cast<size_t>(wplanes) * 3 * 32 * 64 + kF2N0 * 64 + 2 * kF2A0Tile +
-         2 * static_cast<size_t>(planes) * 2 * kF2A1Tile + sizeof(F2Smem) + 64;
+         2 * static_cast<size_t>(planes) * 2 * kF2A1Tile + kF2XStages * kF2XStage + sizeof(F2Smem) + 64;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1681,6 +1730,8 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
   if (fused2) {
+    RISER_REQUIRE((ld_x & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                  "riser_forward: x must be 16-byte aligned with ld_x a multiple of 4 (bulk copies of the signal)");
     pick_fused01(a.planes, a.wplanes)<<<grid, kF2Threads, lp.smem, st>>>(lp.tm_b, a);
     RISER_CUDA_TRY(cudaGetLastError());
     return RISER_OK;
