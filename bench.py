@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--length", type=int, default=LENGTH)
-    ap.add_argument("--precision", type=int, default=None, help="0 F16, 1 F16_W2, 2 F16_X3 (default)")
+    ap.add_argument("--precision", type=int, default=None, help="0 F16, 1 F16_W2, 2 F16_X3, 3 F16_F8; default = riser_b200.model.DEFAULT_PRECISION")
     ap.add_argument("--chunk", type=int, default=None)
     ap.add_argument("--ref-reads", type=int, default=48)
     ap.add_argument("--cpu-sample", type=int, default=96)
@@ -312,7 +312,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f16 operands, f32 accumulate", 1: "f16 (weights hi+lo), f32 accumulate",
-                      2: "f16 hi+lo split (3 tcgen05 passes), f32 accumulate"}[precision],
+                      2: "f16 hi+lo split (3 tcgen05 passes), f32 accumulate",
+                      3: "f16 pass + e4m3 correction pass (hi+lo split, 2 pass-equivalents), f32 accumulate"}[precision],
             "data": "synthetic",
             "config": {"workload": workload_name(B, L), "precision_mode": precision, "chunk": clf.chunk,
                        "cache": "L2 flushed between steps (256 MiB write); inputs 393 MB > L2",
@@ -320,8 +321,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
-                         "executed_tflops": achieved * {0: 1, 1: 2, 2: 3}[precision],
-                         "executed_note": "tcgen05 passes per algorithmic FLOP: 1 (F16), 2 (F16_W2), 3 (F16_X3)",
+                         "executed_tflops": achieved * {0: 1, 1: 2, 2: 3, 3: 2}[precision],
+                         "executed_note": "fp16-pass-equivalents of tcgen05 work per algorithmic FLOP: 1 (F16), "
+                                          "2 (F16_W2), 3 (F16_X3), 2 (F16_F8: one fp16 pass + two e4m3 passes at twice the rate)",
                          "share_of_step": conv_ms / (total_ms / args.steps)},
             "e2e": {"value": reads / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,

@@ -58,8 +58,14 @@ enum { RISER_MODE_ENRICH = 0, RISER_MODE_DEPLETE = 1 };
  *   F16_W2 : two passes; weights split hi + lo fp16 (exact to ~22 bits), only the
  *            activation rounding remains.
  *   F16_X3 : three passes; weights AND activations split hi + lo
- *            (W_hi a_hi + W_lo a_hi + W_hi a_lo): fp32-class results.           */
-enum { RISER_PREC_F16 = 0, RISER_PREC_F16_W2 = 1, RISER_PREC_F16_X3 = 2 };
+ *            (W_hi a_hi + W_lo a_hi + W_hi a_lo): fp32-class results.
+ *   F16_F8 : the fp16 pass plus ONE e4m3 pass (kind::f8f6f4, twice the fp16 rate)
+ *            that carries both correction terms, W_lo a + (W_hi 2^-9)(a_lo 2^9):
+ *            the corrections are ~2^-11 of the result, so 3 mantissa bits suffice
+ *            (format error ~6e-5 on the probabilities).  Two pass-equivalents of
+ *            tensor work instead of three; activation rows are
+ *            [hi fp16 | e4m3(a) | e4m3(a_lo 2^9)] = the bytes of hi + lo.        */
+enum { RISER_PREC_F16 = 0, RISER_PREC_F16_W2 = 1, RISER_PREC_F16_X3 = 2, RISER_PREC_F16_F8 = 3 };
 
 int riser_version(void);
 const char* riser_last_error(void);

@@ -56,6 +56,7 @@ int pick_n_tile(int cout) {
 struct LayerPack {
   int cin = 0, cout = 0, cin_p = 0, cout_p = 0, n_tile = 0, n_tiles = 0;
   __half* w = nullptr;    // [passes][3][cout_p][cin_p] fp16 (layers >= 1)
+  uint8_t* w8 = nullptr;  // F16_F8 mode: [3][cout_p][2*cin_p] e4m3 = [W_lo | W_hi * 2^-9] (correction pass)
   float* w0 = nullptr;    // layer 0 only: fp32 [cout][3]
   float* bias = nullptr;  // fp32 [cout_p], zero padded
   float w_inv_scale = 1.f;  // weights are stored multiplied by a power of two (keeps the fp16 lo
@@ -69,7 +70,8 @@ struct riser_model {
   int n_layers = 0;
   int precision = 0;
   int passes = 1;       // weight planes
-  int act_planes = 1;   // activation planes
+  int act_planes = 1;   // activation planes (F16_F8: 2 = [hi fp16 | a8 e4m3 | lo8 e4m3], same bytes as hi + lo)
+  int f8 = 0;           // RISER_PREC_F16_F8
   int device = 0;
   int sm_count = 148;
   riser::LayerPack layer[riser::kMaxLayers];
@@ -99,6 +101,9 @@ struct ConvArgs {
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
   int k32;                // 1 = 32-channel K blocks: 64-byte rows, SWIZZLE_64B (else 64 / 128 B / SWIZZLE_128B)
+  int kb16;               // K blocks of the fp16 pass (== k_blocks unless f8: then k_blocks - kb16 e4m3 blocks follow)
+  int f8;                 // 1 = RISER_PREC_F16_F8: input rows are [hi fp16 | a8 | lo8], see riser_model_create
+  int out_f8;             // output rows in that format
   // fused layer 0 (layer 1 only): A tiles are computed in-kernel from the normalised signal
   const float* x;
   long long ld_x;
@@ -119,7 +124,7 @@ struct ActivityArgs {
 };
 
 struct LayerPlan {
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_a8, tm_b8;
   ConvArgs args;
   int n_supers_total = 0;
   int rows_per_super = 0;   // flat input rows one work item covers (ms * 128; 510 for the fused layers 0+1)
@@ -148,13 +153,47 @@ struct riser_plan {
 namespace riser {
 namespace {
 
+// F16_F8 activation format: besides the fp16 value h = fp16(r), a row carries a8 = e4m3(r) (the operand of
+// the W_lo correction) and lo8 = e4m3((r - h) * 2^9) (the operand of the W_hi * 2^-9 correction).
+constexpr float kF8LoScale = 512.f;
+template <int N>
+__device__ __forceinline__ void store_f8_planes(const float (&r)[N], const __half2 (&h)[N / 2], uint8_t* a8,
+                                                int lo_stride) {
+  uint32_t pa[N / 4], pl[N / 4];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) {
+    uint32_t wa[2], wl[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 4 * j + 2 * e;
+      const float2 back = __half22float2(h[c / 2]);
+      wa[e] = __nv_cvt_float2_to_fp8x2(make_float2(r[c], r[c + 1]), __NV_SATFINITE, __NV_E4M3);
+      wl[e] = __nv_cvt_float2_to_fp8x2(make_float2((r[c] - back.x) * kF8LoScale, (r[c + 1] - back.y) * kF8LoScale),
+                                       __NV_SATFINITE, __NV_E4M3);
+    }
+    pa[j] = wa[0] | (wa[1] << 16);
+    pl[j] = wl[0] | (wl[1] << 16);
+  }
+  if (N == 8) {
+    *reinterpret_cast<uint2*>(a8) = make_uint2(pa[0], pa[1]);
+    *reinterpret_cast<uint2*>(a8 + lo_stride) = make_uint2(pl[0], pl[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N / 16; ++j) {
+      *reinterpret_cast<uint4*>(a8 + 16 * j) = make_uint4(pa[4 * j], pa[4 * j + 1], pa[4 * j + 2], pa[4 * j + 3]);
+      *reinterpret_cast<uint4*>(a8 + lo_stride + 16 * j) =
+          make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // layer 0: x fp32 [B, ld_x] -> act_1 [B*Lp1][cout_p] fp16.  One thread per (output row,
 // 8-channel group): consecutive lanes write consecutive 16-byte chunks (coalesced).
 __global__ void __launch_bounds__(256)
 layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ len0,
               const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ out,
-              int B, int Lp1, int cout, int cout_p, int planes) {
+              int B, int Lp1, int cout, int cout_p, int planes, int f8) {
   __shared__ float sw[64 * 3];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < cout_p * 3; i += blockDim.x) sw[i] = (i < cout * 3) ? w[i] : 0.f;
@@ -169,9 +208,15 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
     const int tp = static_cast<int>(r - static_cast<uint32_t>(b) * Lp1);
     const int L = len0[b];
     uint4* o = reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * cout_p * planes) + c8;
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + static_cast<int64_t>(r) * cout_p * 4 + 2 * cout_p + c8 * 8;
     if (tp >= (L >> 1)) {
       *o = make_uint4(0, 0, 0, 0);
-      if (planes == 2) o[groups] = make_uint4(0, 0, 0, 0);
+      if (f8) {
+        *reinterpret_cast<uint2*>(o8) = make_uint2(0, 0);
+        *reinterpret_cast<uint2*>(o8 + cout_p) = make_uint2(0, 0);
+      } else if (planes == 2) {
+        o[groups] = make_uint4(0, 0, 0, 0);
+      }
       continue;
     }
     const float* xr = x + static_cast<int64_t>(b) * ld_x;
@@ -180,6 +225,7 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
     const float2 x01 = *reinterpret_cast<const float2*>(xr + t);
     const float x2 = (t + 2 < L) ? xr[t + 2] : 0.f;
     __half2 h[4], hl[4];
+    float vv[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v[2];
@@ -194,9 +240,12 @@ layer0_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restri
       h[j] = __floats2half2_rn(v[0], v[1]);
       const float2 back = __half22float2(h[j]);
       hl[j] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
+      vv[2 * j] = v[0];
+      vv[2 * j + 1] = v[1];
     }
     *o = *reinterpret_cast<uint4*>(h);
-    if (planes == 2) o[groups] = *reinterpret_cast<uint4*>(hl);
+    if (f8) store_f8_planes<8>(vv, h, o8, cout_p);
+    else if (planes == 2) o[groups] = *reinterpret_cast<uint4*>(hl);
   }
 }
 
@@ -238,7 +287,8 @@ __device__ __forceinline__ __half2 sat_half2(float a, float b) {
 // columns 0..7 of the chunk, the odd lane columns 8..15.
 __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const float* bias_s, int col0,
                                                  bool odd, bool valid, bool writable, void* out_row,
-                                                 bool out_fp32, int lo_plane_off, float inv_scale) {
+                                                 bool out_fp32, int lo_plane_off, float inv_scale,
+                                                 uint8_t* f8_row = nullptr, int f8_stride = 0) {
   float r[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -277,6 +327,7 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
       }
       *reinterpret_cast<uint4*>(oh + lo_plane_off) = *reinterpret_cast<const uint4*>(l);
     }
+    if (f8_row) store_f8_planes<8>(r, h, f8_row + c, f8_stride);
   }
 }
 
@@ -329,9 +380,10 @@ struct ItemFlags {
   }
 };
 
-template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false, bool K32 = false>
+template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false, bool K32 = false, bool F8 = false>
 __global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : 64 + 128 * kMaxEpiSets, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_b8,
                const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment by OFFSET (not by casting through an integer): keeps the pointer in the
@@ -358,6 +410,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (F8) {
+      tma_prefetch_desc(&tm_a8);
+      tma_prefetch_desc(&tm_b8);
+    }
     for (int i = 0; i < a.a_stages; ++i) {
       mbar_init(&s.a_full[i], FUSED ? kCvtThreads : 1);
       mbar_init(&s.a_empty[i], 1);
@@ -389,9 +445,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         mbar_arrive_expect_tx(&s.w_full, static_cast<uint32_t>(b_region_bytes));
         for (int wp = 0; wp < WPLANES; ++wp)
           for (int tap = 0; tap < 3; ++tap)
-            for (int kb = 0; kb < a.k_blocks; ++kb)
-              tma_load_2d(b_region + static_cast<size_t>((wp * 3 + tap) * a.k_blocks + kb) * b_bytes, &tm_b,
-                          &s.w_full, kb * kKElems, (wp * 3 + tap) * a.cout_p);
+            for (int kb = 0; kb < a.k_blocks; ++kb) {
+              unsigned char* dst = b_region + static_cast<size_t>((wp * 3 + tap) * a.k_blocks + kb) * b_bytes;
+              if (F8 && kb >= a.kb16)
+                tma_load_2d(dst, &tm_b8, &s.w_full, (kb - a.kb16) * kRowBytes, tap * a.cout_p);
+              else
+                tma_load_2d(dst, &tm_b, &s.w_full, kb * kKElems, (wp * 3 + tap) * a.cout_p);
+            }
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -409,9 +469,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int ms = 0; ms < MS; ++ms)
 #pragma unroll
-            for (int ap = 0; ap < PLANES; ++ap)
-              tma_load_2d(dst + (ms * PLANES + ap) * kATile, &tm_a, &s.a_full[sa],
-                          ap * a.cin_p + kb * kKElems, m0 + ms * kBlockM);
+            for (int ap = 0; ap < PLANES; ++ap) {
+              if (F8 && kb >= a.kb16)   // e4m3 part of the row: bytes [2*cin_p, 4*cin_p)
+                tma_load_2d(dst + (ms * PLANES + ap) * kATile, &tm_a8, &s.a_full[sa],
+                            2 * a.cin_p + (kb - a.kb16) * kRowBytes, m0 + ms * kBlockM);
+              else
+                tma_load_2d(dst + (ms * PLANES + ap) * kATile, &tm_a, &s.a_full[sa],
+                            ap * a.cin_p + kb * kKElems, m0 + ms * kBlockM);
+            }
           if (++sa == a.a_stages) {
             sa = 0;
             pa ^= 1;
@@ -423,8 +488,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               for (int wp = 0; wp < WPLANES; ++wp) {
                 mbar_wait(&s.b_empty[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&s.b_full[sb], b_bytes);
-                tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * kKElems,
-                            (wp * 3 + tap) * a.cout_p + n0);
+                if (F8 && kb >= a.kb16)
+                  tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b8, &s.b_full[sb],
+                              (kb - a.kb16) * kRowBytes, tap * a.cout_p + n0);
+                else
+                  tma_load_2d(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * kKElems,
+                              (wp * 3 + tap) * a.cout_p + n0);
                 if (++sb == a.b_stages) {
                   sb = 0;
                   pb ^= 1;
@@ -444,7 +513,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       int sa = 0, sb = 0, stage = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
       const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
-      const int nk_last = (a.cin_p - (a.k_blocks - 1) * kKElems) / 16;
+      const int nk_last = (a.cin_p - (a.kb16 - 1) * kKElems) / 16;
+      const int nk_last8 = F8 ? (2 * a.cin_p - (a.k_blocks - a.kb16 - 1) * kRowBytes) / 32 : 0;
       const uint32_t acc_stride = MS * a.acc_cols;
       ItemCursor cur(blockIdx.x, gridDim.x, a.n_tiles, a.super0);
       ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
@@ -452,7 +522,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (!fl.take(cur, item + gridDim.x < n_items)) continue;
         const uint32_t d_base = tmem_base + stage * acc_stride;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
-          const int nk = (kb == a.k_blocks - 1) ? nk_last : (kKElems / 16);
+          const bool is8 = F8 && kb >= a.kb16;     // e4m3 correction blocks follow the fp16 blocks
+          const int nk = is8 ? ((kb == a.k_blocks - 1) ? nk_last8 : (kKElems / 16))
+                             : ((kb == a.kb16 - 1) ? nk_last : (kKElems / 16));
           mbar_wait(&s.a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_addr = a_ring_addr + sa * kAGroupBytes;
@@ -482,9 +554,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             : sw_desc<K32>(a_addr + (ms * PLANES + ap) * kATile + tap * kRowBytes);
 #pragma unroll
                   for (int k = 0; k < kKElems / 16; ++k)
-                    if (k < nk)
-                      umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
-                               (kb | tap | wp | ap | k) != 0);
+                    if (k < nk) {
+                      if (is8)
+                        umma_f8(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
+                      else
+                        umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
+                                 (kb | tap | wp | ap | k) != 0);
+                    }
                 }
               }
               if (!RESIDENT) {
@@ -599,7 +675,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int epi_threads = 128 * a.epi_sets;
     const bool odd = lane & 1;
     const int row_elems = a.cout_p * a.out_planes;
-    const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
+    const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
     const int n_chunks = a.n_tile >> 4;
     const bool single_n = (a.n_tiles == 1);
     if (single_n) {
@@ -654,8 +730,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           uint32_t v[16];
           tmem_ld_32x16(t_addr + c * 16, v);
           tmem_ld_wait();
+          uint8_t* f8_row = nullptr;
+          if (F8 && a.out_f8)
+            f8_row = static_cast<uint8_t*>(a.out) + out_row[ms] * row_elems * 2 + 2 * a.cout_p + n0;
           epilogue_chunk16(v, bias_s, c * 16, odd, valid[ms], writable[ms], orow, a.out_fp32, lo_off,
-                           a.w_inv_scale);
+                           a.w_inv_scale, f8_row, a.cout_p);
         }
         // this sub-tile's accumulator is drained: the MMA warp may start the next item on it
         tc_fence_before();
@@ -677,7 +756,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
 }
 
-typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvArgs);
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const ConvArgs);
 
 template <int MS, bool RESIDENT, bool FUSED, bool K32>
 ConvKernelFn pick_conv_planes(int planes, int wplanes) {
@@ -701,7 +781,21 @@ ConvKernelFn pick_conv_k(int ms, int planes, int wplanes, int resident, int fuse
   if (ms == 2) return pick_conv_planes<2, false, false, K32>(planes, wplanes);
   return pick_conv_planes<1, false, false, K32>(planes, wplanes);
 }
-ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0, int k32 = 0) {
+// F16_F8 mode: one activation / weight plane per K block, the e4m3 correction blocks after the fp16 ones
+template <bool K32>
+ConvKernelFn pick_conv_f8(int ms, int resident) {
+  if (resident) {
+    if (ms == 4) return conv_tc_kernel<4, 1, 1, true, false, K32, true>;
+    if (ms == 2) return conv_tc_kernel<2, 1, 1, true, false, K32, true>;
+    return conv_tc_kernel<1, 1, 1, true, false, K32, true>;
+  }
+  if (ms == 4) return conv_tc_kernel<4, 1, 1, false, false, K32, true>;
+  if (ms == 2) return conv_tc_kernel<2, 1, 1, false, false, K32, true>;
+  return conv_tc_kernel<1, 1, 1, false, false, K32, true>;
+}
+ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int fused = 0, int k32 = 0,
+                              int f8 = 0) {
+  if (f8) return k32 ? pick_conv_f8<true>(ms, resident) : pick_conv_f8<false>(ms, resident);
   return k32 ? pick_conv_k<true>(ms, planes, wplanes, resident, fused)
              : pick_conv_k<false>(ms, planes, wplanes, resident, fused);
 }
@@ -772,12 +866,17 @@ struct F2Iter {
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-template <int PLANES, int WPLANES>
+// MODE: 0 = F16, 1 = F16_W2 (weights hi + lo), 2 = F16_X3 (weights and activations hi + lo),
+// 3 = F16_F8 (fp16 pass + e4m3 correction pass: second tile of a stage / second weight set are bytes)
+template <int MODE>
 __global__ void __launch_bounds__(kF2Threads, 1)
-fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
+fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b8, const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  constexpr uint32_t kW1Bytes = WPLANES * 3 * 32 * 64;
+  constexpr bool F8 = (MODE == 3);
+  constexpr int PLANES = (MODE >= 2) ? 2 : 1;
+  constexpr int WPLANES = (MODE == 1 || MODE == 2) ? 2 : 1;
+  constexpr uint32_t kW1Bytes = (F8 ? 2 : WPLANES) * 3 * 32 * 64;
   constexpr uint32_t kB0Bytes = kF2N0 * 64;
   constexpr uint32_t kA1Stage = PLANES * 2 * kF2A1Tile;
   unsigned char* w1 = base;
@@ -860,6 +959,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
       for (int wp = 0; wp < WPLANES; ++wp)
         for (int tap = 0; tap < 3; ++tap)
           tma_load_2d(w1 + (wp * 3 + tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+      if (F8)
+        for (int tap = 0; tap < 3; ++tap)
+          tma_load_2d(w1 + (3 + tap) * 2048, &tm_b8, &s.w_full, 0, tap * a.cout_p);
       // Stage slot of pair i (i = -2 .. 256) is 16*(i+2): its four samples x[4t .. 4t+3].  An item spans at
       // most two reads (a read has more pairs than an item); pairs with 4t >= ld_x are not loaded (they lie
       // beyond every valid length and are masked by cvt1).
@@ -951,13 +1053,19 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
               for (int wp = 0; wp < WPLANES; ++wp) {
                 const uint64_t db = sw_desc<true>(w1_addr + (wp * 3 + tap) * 2048);
 #pragma unroll
-                for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {
+                for (int ap = 0; ap < ((wp == 0 && !F8) ? PLANES : 1); ++ap) {
                   const uint64_t da =
                       sw_desc<true>(a1s + (ap * 2 + par) * kF2A1Tile + (sub * 128 + shift) * 64);
 #pragma unroll
                   for (int k = 0; k < 2; ++k)
                     umma_f16(d, da + 2 * k, db + 2 * k, a.idesc, (tap | wp | ap | k) != 0);
                 }
+              }
+              if (F8) {   // correction pass: [a8 | lo8] x [W_lo | W_hi * 2^-9], 64 e4m3 per row = 2 k-steps
+                const uint64_t db = sw_desc<true>(w1_addr + (3 + tap) * 2048);
+                const uint64_t da = sw_desc<true>(a1s + (2 + par) * kF2A1Tile + (sub * 128 + shift) * 64);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_f8(d, da + 2 * k, db + 2 * k, a.idesc, 1);
               }
             }
           }
@@ -1068,28 +1176,51 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
         const int row = sub * 128 + 32 * q + lane;
         unsigned char* rp = tile_hi + row * 64;
         const int sw = (row >> 1) & 3;
+        float v[24];
 #pragma unroll
-        for (int c8 = 0; c8 < 3; ++c8) {
-          __half2 hv[4], lv[4];
+        for (int c = 0; c < 24; ++c) {
+          const float ev = __uint_as_float(c < 16 ? e0[c & 15] : e1[c & 7]);
+          const float ov = __uint_as_float(c < 16 ? o0[c & 15] : o1[c & 7]);
+          v[c] = fmaxf(fmaxf(ev, ov), 0.f);
+        }
+        __half2 hv[12];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float v[2];
+        for (int j = 0; j < 12; ++j) hv[j] = sat_half2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+        for (int c8 = 0; c8 < 3; ++c8)
+          *reinterpret_cast<uint4*>(rp + ((c8 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(hv + 4 * c8);
+        if (PLANES == 2 && !F8) {
+          __half2 lv[12];
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const float2 back = __half22float2(hv[j]);
+            lv[j] = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < 3; ++c8)
+            *reinterpret_cast<uint4*>(rp + 2 * kF2A1Tile + ((c8 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(lv + 4 * c8);
+        }
+        if (F8) {   // byte row: [a8 ch 0..31 | lo8 ch 0..31], channels 24..31 are zero
+          uint32_t pa[6], pl[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            uint32_t wa[2], wl[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int c = c8 * 8 + 2 * j + e;
-              const float ev = __uint_as_float(c < 16 ? e0[c & 15] : e1[c & 7]);
-              const float ov = __uint_as_float(c < 16 ? o0[c & 15] : o1[c & 7]);
-              v[e] = fmaxf(fmaxf(ev, ov), 0.f);
+              const int c = 4 * j + 2 * e;
+              const float2 back = __half22float2(hv[c / 2]);
+              wa[e] = __nv_cvt_float2_to_fp8x2(make_float2(v[c], v[c + 1]), __NV_SATFINITE, __NV_E4M3);
+              wl[e] = __nv_cvt_float2_to_fp8x2(
+                  make_float2((v[c] - back.x) * kF8LoScale, (v[c + 1] - back.y) * kF8LoScale), __NV_SATFINITE, __NV_E4M3);
             }
-            hv[j] = sat_half2(v[0], v[1]);
-            if (PLANES == 2) {
-              const float2 back = __half22float2(hv[j]);
-              lv[j] = __floats2half2_rn(v[0] - back.x, v[1] - back.y);
-            }
+            pa[j] = wa[0] | (wa[1] << 16);
+            pl[j] = wl[0] | (wl[1] << 16);
           }
-          const int off = (c8 ^ sw) << 4;
-          *reinterpret_cast<uint4*>(rp + off) = *reinterpret_cast<const uint4*>(hv);
-          if (PLANES == 2) *reinterpret_cast<uint4*>(rp + 2 * kF2A1Tile + off) = *reinterpret_cast<const uint4*>(lv);
+          unsigned char* rp8 = rp + 2 * kF2A1Tile;
+          *reinterpret_cast<uint4*>(rp8 + ((0 ^ sw) << 4)) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+          *reinterpret_cast<uint4*>(rp8 + ((1 ^ sw) << 4)) = make_uint4(pa[4], pa[5], 0u, 0u);
+          *reinterpret_cast<uint4*>(rp8 + ((2 ^ sw) << 4)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          *reinterpret_cast<uint4*>(rp8 + ((3 ^ sw) << 4)) = make_uint4(pl[4], pl[5], 0u, 0u);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1101,7 +1232,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
     const int q = warp & 3;
     const int sub = (warp - 12) >> 2;
     const int row_elems = a.cout_p * a.out_planes;
-    const int lo_off = (a.out_planes == 2) ? a.cout_p : 0;
+    const int lo_off = (a.out_planes == 2 && !F8) ? a.cout_p : 0;
     const float inv_scale = a.w_inv_scale;
     F2Iter iter(flags0, n_items);
     int k = 0;
@@ -1164,6 +1295,8 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
             ol[0] = *reinterpret_cast<const uint4*>(lv);
             ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
           }
+          if (F8)
+            store_f8_planes<16>(r, hv, reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c16 * 16, a.cout_p);
         }
         __syncwarp();
       }
@@ -1178,11 +1311,12 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
   }
 }
 
-typedef void (*FusedKernelFn)(const CUtensorMap, const ConvArgs);
-FusedKernelFn pick_fused01(int planes, int wplanes) {
-  if (planes == 1 && wplanes == 1) return fused01_kernel<1, 1>;
-  if (planes == 1 && wplanes == 2) return fused01_kernel<1, 2>;
-  return fused01_kernel<2, 2>;
+typedef void (*FusedKernelFn)(const CUtensorMap, const CUtensorMap, const ConvArgs);
+FusedKernelFn pick_fused01(int mode) {
+  if (mode == 0) return fused01_kernel<0>;
+  if (mode == 1) return fused01_kernel<1>;
+  if (mode == 2) return fused01_kernel<2>;
+  return fused01_kernel<3>;
 }
 size_t fused01_smem(int planes, int wplanes) {
   return 1024 + static_cast<size_t>(wplanes) * 3 * 32 * 64 + kF2N0 * 64 + 2 * kF2A0Tile +
@@ -1330,6 +1464,24 @@ int make_tmap(CUtensorMap* tm, void* ptr, uint64_t cols, uint64_t rows, uint32_t
   return RISER_OK;
 }
 
+// bytes [rows][cols] with row pitch `stride`, zero OOB fill; box (128 B or -- k32 -- 64 B, box_rows), swizzled alike
+int make_tmap8(CUtensorMap* tm, void* ptr, uint64_t cols, uint64_t stride, uint64_t rows, uint32_t box_rows, bool k32) {
+  EncodeTiledFn enc;
+  int st = get_encode_fn(&enc);
+  if (st) return st;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {stride};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(k32 ? 64 : 128), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(RISER_ECUDA, "cuTensorMapEncodeTiled (bytes) failed (%d) for %llu x %llu box %u", static_cast<int>(r),
+                static_cast<unsigned long long>(cols), static_cast<unsigned long long>(rows), box_rows);
+  return RISER_OK;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 void plan_lengths(const riser_model* m, int max_len, int* Lmax, int* Lp) {
@@ -1369,7 +1521,7 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   RISER_REQUIRE(out && channels && conv_w && conv_b && fc_w && fc_b, "riser_model_create: null pointer");
   RISER_REQUIRE(n_layers >= 2 && n_layers <= kMaxLayers, "riser_model_create: n_layers %d outside [2, %d]",
                 n_layers, kMaxLayers);
-  RISER_REQUIRE(precision >= RISER_PREC_F16 && precision <= RISER_PREC_F16_X3,
+  RISER_REQUIRE(precision >= RISER_PREC_F16 && precision <= RISER_PREC_F16_F8,
                 "riser_model_create: unknown precision %d", precision);
   RISER_REQUIRE(channels[0] <= 64, "riser_model_create: layer 0 supports at most 64 output channels");
   RISER_CUDA_TRY(cudaSetDevice(device));
@@ -1380,8 +1532,9 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   riser_model* m = new riser_model();
   m->n_layers = n_layers;
   m->precision = precision;
-  m->passes = (precision == RISER_PREC_F16) ? 1 : 2;           // weight planes (hi [, lo])
-  m->act_planes = (precision == RISER_PREC_F16_X3) ? 2 : 1;    // activation planes (hi [, lo])
+  m->f8 = (precision == RISER_PREC_F16_F8) ? 1 : 0;
+  m->passes = (precision == RISER_PREC_F16 || m->f8) ? 1 : 2;  // fp16 weight planes (hi [, lo])
+  m->act_planes = (precision == RISER_PREC_F16_X3 || m->f8) ? 2 : 1;   // activation planes (hi [, lo])
   m->device = device;
   cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
   int cin = 1, cin_p = 1;
@@ -1404,6 +1557,7 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
       // [plane][tap][cout_p][cin_p]: tap-major so that one 2-D tensor map serves all taps
       const size_t per_pass = static_cast<size_t>(3) * L.cout_p * L.cin_p;
       std::vector<__half> w(per_pass * m->passes, __float2half(0.f));
+      std::vector<uint8_t> w8(m->f8 ? 2 * per_pass : 0, 0);
       const float* src = conv_w[i];   // [cout][cin][3]
       float wmax = 0.f;
       for (size_t k = 0; k < static_cast<size_t>(L.cout) * L.cin * 3; ++k) wmax = std::max(wmax, std::fabs(src[k]));
@@ -1423,7 +1577,16 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
             const size_t idx = (static_cast<size_t>(tap) * L.cout_p + co) * L.cin_p + ci;
             w[idx] = hi;
             if (m->passes == 2) w[per_pass + idx] = __float2half_rn(v - __half2float(hi));
+            if (m->f8) {   // correction operands: [W_lo | W_hi * 2^-9] e4m3 (pair with a8 and lo8 * 2^9)
+              const size_t i8 = (static_cast<size_t>(tap) * L.cout_p + co) * (2 * L.cin_p) + ci;
+              w8[i8] = __nv_cvt_float_to_fp8(v - __half2float(hi), __NV_SATFINITE, __NV_E4M3);
+              w8[i8 + L.cin_p] = __nv_cvt_float_to_fp8(v * (1.f / kF8LoScale), __NV_SATFINITE, __NV_E4M3);
+            }
           }
+      if (m->f8) {
+        RISER_CUDA_TRY(cudaMalloc(&L.w8, w8.size()));
+        RISER_CUDA_TRY(cudaMemcpy(L.w8, w8.data(), w8.size(), cudaMemcpyHostToDevice));
+      }
       RISER_CUDA_TRY(cudaMalloc(&L.w, sizeof(__half) * w.size()));
       RISER_CUDA_TRY(cudaMemcpy(L.w, w.data(), sizeof(__half) * w.size(), cudaMemcpyHostToDevice));
     }
@@ -1443,6 +1606,7 @@ extern "C" int riser_model_destroy(riser_model* m) {
   if (!m) return RISER_OK;
   for (int i = 0; i < m->n_layers; ++i) {
     cudaFree(m->layer[i].w);
+    cudaFree(m->layer[i].w8);
     cudaFree(m->layer[i].w0);
     cudaFree(m->layer[i].bias);
   }
@@ -1530,6 +1694,13 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
                        a_box_rows, k32);
     if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile, k32);
+    if (!st && m->f8) {
+      st = make_tmap8(&lp.tm_a8, p->ws + p->act_off[i], 4ull * L.cin_p, 4ull * L.cin_p, rows_in, a_box_rows, k32);
+      if (!st) st = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, L.n_tile, k32);
+    } else {
+      lp.tm_a8 = lp.tm_a;
+      lp.tm_b8 = lp.tm_b;
+    }
     if (st) {
       delete p;
       return st;
@@ -1546,9 +1717,13 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.cout_p = L.cout_p;
     a.n_tile = L.n_tile;
     a.n_tiles = L.n_tiles;
-    a.k_blocks = (L.cin_p + k_elems - 1) / k_elems;
+    a.kb16 = (L.cin_p + k_elems - 1) / k_elems;
+    a.k_blocks = a.kb16 + (m->f8 ? (2 * L.cin_p + row_bytes - 1) / row_bytes : 0);
     a.k32 = k32 ? 1 : 0;
-    a.planes = m->act_planes;
+    a.f8 = m->f8;
+    a.out_f8 = (m->f8 && !last) ? 1 : 0;
+    const int kplanes = m->f8 ? 1 : m->act_planes;     // activation tiles per K block
+    a.planes = kplanes;
     a.wplanes = m->passes;
     a.out_fp32 = last ? 1 : 0;
     a.out_planes = last ? 1 : m->act_planes;
@@ -1562,7 +1737,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
     const size_t avail = static_cast<size_t>(max_smem) - fixed;
     const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
-    const size_t a_group1 = static_cast<size_t>(m->act_planes) * 136 * row_bytes;
+    const size_t a_group1 = static_cast<size_t>(kplanes) * 136 * row_bytes;
     if (allow_resident && L.n_tiles == 1 && w_all + 2 * a_group1 <= avail) {
       // resident weights; as many 128-row sub-tiles per work item as leave >= 2 accumulator
       // stages and >= 2 A groups in flight (amortises the per-item bookkeeping of small-N layers)
@@ -1578,7 +1753,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b_stages = 1;
       a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_all) / (a.ms * a_group1)));
       lp.smem = fixed + w_all + static_cast<size_t>(a.a_stages) * a.ms * a_group1;
-      if (i == 1 && L.cin_p == 32 && want_fuse == 1) {
+      if (i == 1 && L.cin_p == 32 && want_fuse == 1 && !m->f8) {
         // fused layer 0: A tiles are written by converter warps; one contiguous
         // (ms*128 + 8)-row tile per plane and stage
         for (int ms = want_ms; ms >= 1; ms >>= 1) {
@@ -1626,7 +1801,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b0 = m->layer[0].bias;
       a.cout0 = m->layer[0].cout;
       lp.rows_per_super = 2 * kF2Pairs;
-      lp.smem = fused01_smem(m->act_planes, m->passes);
+      lp.smem = fused01_smem(m->act_planes, m->f8 ? 2 : m->passes);
+      a.planes = m->act_planes;     // fused01_kernel's own modes (see pick_fused01)
     }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
   }
@@ -1656,9 +1832,14 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
               reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, mode >= 1,
                                                              mode == 2, k32v)),
               cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  for (int pl = 0; pl < 3; ++pl)
-    RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl == 2 ? 2 : 1, pl == 0 ? 1 : 2)),
+  for (int pl = 0; pl < 4; ++pl)
+    RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl)),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  for (int k32v = 0; k32v < 2; ++k32v)
+    for (int ms = 1; ms <= 4; ms <<= 1)
+      for (int res = 0; res < 2; ++res)
+        RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, 1, 1, res, 0, k32v, 1)),
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   *out = p;
   return RISER_OK;
 }
@@ -1705,7 +1886,7 @@ int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32
   __half* out = reinterpret_cast<__half*>(p->ws + p->act_off[1]) +
                 static_cast<int64_t>(b0) * p->Lp[1] * L.cout_p * m->act_planes;
   layer0_kernel<<<grid, 256, 0, st>>>(x + static_cast<int64_t>(b0) * ld_x, ld_x, len + b0, L.w0, L.bias, out, nb,
-                                      p->Lp[1], L.cout, L.cout_p, m->act_planes);
+                                      p->Lp[1], L.cout, L.cout_p, m->act_planes, m->f8);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
@@ -1732,11 +1913,12 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   if (fused2) {
     RISER_REQUIRE((ld_x & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                   "riser_forward: x must be 16-byte aligned with ld_x a multiple of 4 (bulk copies of the signal)");
-    pick_fused01(a.planes, a.wplanes)<<<grid, kF2Threads, lp.smem, st>>>(lp.tm_b, a);
+    pick_fused01(a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(
+        lp.tm_b, lp.tm_b8, a);
     RISER_CUDA_TRY(cudaGetLastError());
     return RISER_OK;
   }
-  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_b, a);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32, a.f8)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

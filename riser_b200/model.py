@@ -17,6 +17,7 @@ from . import _lib
 PREC_F16 = 0       # one tcgen05 pass, fp16 weights
 PREC_F16_W2 = 1    # two passes, weights split hi + lo (exact to ~22 bits)
 PREC_F16_X3 = 2    # three passes, weights and activations split hi + lo: fp32-class
+PREC_F16_F8 = 3    # fp16 pass + one e4m3 pass carrying both hi/lo correction terms (2 pass-equivalents)
 DEFAULT_PRECISION = PREC_F16_X3
 MIN_LENGTH = 4096  # riser/preprocess.py:8 -- 12 stride-2 pools
 DEFAULT_CHUNK = 0    # 0 = whole batch in one plan (the plan chunks the early layers itself)
@@ -53,6 +54,11 @@ class Plan:
         if planes == 2 and i != n_layers:      # hi + lo planes side by side
             half = cp // 2
             return full[:, :, :c].float() + full[:, :, half:half + c].float()
+        if planes == 3 and i != n_layers:      # F16_F8 rows: [hi fp16 | a8 e4m3 | lo8 e4m3 = (a - hi) * 2^9]
+            half = cp // 2
+            raw = self.workspace[off:off + nbytes].view(self.B, rows, cp * 2)
+            lo8 = raw[:, :, 3 * half:3 * half + c].contiguous().view(torch.float8_e4m3fn).float()
+            return full[:, :, :c].float() + lo8 / 512.0
         return full[:, :, :c]
 
     def __del__(self):
