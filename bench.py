@@ -318,7 +318,7 @@ def main():
             "config": {"workload": workload_name(B, L), "precision_mode": precision, "chunk": clf.chunk,
                        "cache": "L2 flushed between steps (256 MiB write); inputs 393 MB > L2",
                        "flops_per_read": flops_per_read(L), "decisions_made": n_dec},
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
+            "roofline": {"bound": "tensor", "kernel": "fused01_kernel + conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "executed_tflops": achieved * {0: 1, 1: 2, 2: 3, 3: 2}[precision],

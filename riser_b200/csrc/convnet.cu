@@ -59,6 +59,8 @@ struct LayerPack {
   uint8_t* w8 = nullptr;  // F16_F8 mode: [3][cout_p][2*cin_p] e4m3 = [W_lo | W_hi * 2^-9] (correction pass)
   float* w0 = nullptr;    // layer 0 only: fp32 [cout][3]
   float* bias = nullptr;  // fp32 [cout_p], zero padded
+  int passes = 1;           // fp16 weight planes of this layer (hi [, lo])
+  int f8 = 0;               // this layer's input rows are [hi | a8 | lo8] and its corrections run as one e4m3 pass
   float w_inv_scale = 1.f;  // weights are stored multiplied by a power of two (keeps the fp16 lo
                             // plane out of the subnormal range); the epilogue undoes it exactly
 };
@@ -71,7 +73,9 @@ struct riser_model {
   int precision = 0;
   int passes = 1;       // weight planes
   int act_planes = 1;   // activation planes (F16_F8: 2 = [hi fp16 | a8 e4m3 | lo8 e4m3], same bytes as hi + lo)
-  int f8 = 0;           // RISER_PREC_F16_F8
+  int f8 = 0;           // RISER_PREC_F16_F8: layers >= f8_from take the e4m3 correction pass, earlier ones
+                        // (epilogue-bound, not tensor-bound) keep the hi + lo fp16 planes of F16_X3
+  int f8_from = 0;
   int device = 0;
   int sm_count = 148;
   riser::LayerPack layer[riser::kMaxLayers];
@@ -731,7 +735,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           tmem_ld_32x16(t_addr + c * 16, v);
           tmem_ld_wait();
           uint8_t* f8_row = nullptr;
-          if (F8 && a.out_f8)
+          if (a.out_f8)
             f8_row = static_cast<uint8_t*>(a.out) + out_row[ms] * row_elems * 2 + 2 * a.cout_p + n0;
           epilogue_chunk16(v, bias_s, c * 16, odd, valid[ms], writable[ms], orow, a.out_fp32, lo_off,
                            a.w_inv_scale, f8_row, a.cout_p);
@@ -823,6 +827,9 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
 //   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
 //   warps 4..11   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
 //   warps 12..19  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
+#ifndef RISER_DBG
+#define RISER_DBG 0      // timing experiments only (wrong results): 1 = one MMA per layer-1 accumulator, 2 = no global
+#endif                   // stores, 4 = mid-epilogue skips its TMEM loads, 8 = epilogue skips its TMEM loads
 constexpr int kF2Pairs = 255;
 constexpr int kF2Threads = 640;
 constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shifted taps of row 255 touch
@@ -831,6 +838,7 @@ constexpr int kF2N0 = 48;
 constexpr int kF2D0Col = 256;              // TMEM: layer-1 accumulators [0,256), layer-0 at 256 + 48*k
 constexpr int kF2CvtThreads = 64;
 constexpr int kF2XStages = 4;
+constexpr int kF2MaxLocalItems = 2048;   // work items per CTA whose activity flags fit the shared-memory copy
 constexpr uint32_t kF2XStage = 260 * 16;     // pairs i = -2 .. 256 (4 samples each) + pad
 
 struct F2Smem {
@@ -842,22 +850,21 @@ struct F2Smem {
   uint64_t d1_full[2], d1_empty[2][2];
   uint32_t tmem_base;
   alignas(16) float bias[32];
+  uint8_t my_flags[kF2MaxLocalItems];     // activity flags of this CTA's items (item = blockIdx.x + i * gridDim.x)
 };
 
-// Active work items of this CTA in order; the next item's flag is loaded one item ahead.
+// Active work items of this CTA in order.  The flags of the CTA's own items are staged in shared memory once
+// (a global load per item would sit on the critical path of the single-thread roles).
 struct F2Iter {
-  const uint8_t* flags;
-  int item, n_items, step;
-  uint32_t f_next;
-  __device__ __forceinline__ F2Iter(const uint8_t* f, int n) : flags(f), item(blockIdx.x), n_items(n), step(gridDim.x) {
-    f_next = (flags && item < n_items) ? __ldg(flags + item) : 1u;
-  }
+  const uint8_t* local;      // shared-memory copy, or nullptr = every item is active
+  int i, item, n_items, step;
+  __device__ __forceinline__ F2Iter(const uint8_t* l, int n) : local(l), i(0), item(blockIdx.x), n_items(n), step(gridDim.x) {}
   __device__ __forceinline__ int take() {
     while (item < n_items) {
       const int cur = item;
-      const uint32_t f = f_next;
+      const bool f = local ? (local[i] != 0) : true;
       item += step;
-      f_next = (flags && item < n_items) ? __ldg(flags + item) : 1u;
+      ++i;
       if (f) return cur;
     }
     return -1;
@@ -891,6 +898,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
   const int n_items = a.n_supers;
   const int n_pairs = a.rows_in >> 1;
   const uint8_t* flags0 = a.flags ? a.flags + a.super0 : nullptr;
+  const uint8_t* flags_l = flags0 ? s.my_flags : nullptr;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_b);
@@ -920,6 +928,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
   for (uint32_t i = threadIdx.x; i < (2 * kF2A0Tile + 2 * kA1Stage + kF2XStages * kF2XStage) / 16; i += kF2Threads)
     reinterpret_cast<uint4*>(a0_ring)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 32) s.bias[threadIdx.x] = a.bias[threadIdx.x];
+  if (flags0)
+    for (int i = threadIdx.x, it = blockIdx.x + threadIdx.x * gridDim.x; it < n_items; i += kF2Threads, it += kF2Threads * gridDim.x)
+      s.my_flags[i] = flags0[it];
   if (threadIdx.x < kF2N0) {
     // layer-0 B operand, row n: channel n % 24 at conv position 2p + n / 24 (SWIZZLE_64B rows)
     const int n = threadIdx.x, c = n % 24, odd = n / 24;
@@ -956,17 +967,19 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     // ===================== producer: weights once, then the signal segment of every item =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(&s.w_full, kW1Bytes);
+      // taps are stored in REVERSE order (slot 2 - tap): [w2; w1] and [w1; w0] are then contiguous 64-row B
+      // operands, so one N = 64 MMA feeds the even and the odd conv position from the same A rows
       for (int wp = 0; wp < WPLANES; ++wp)
         for (int tap = 0; tap < 3; ++tap)
-          tma_load_2d(w1 + (wp * 3 + tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+          tma_load_2d(w1 + (wp * 3 + 2 - tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
       if (F8)
         for (int tap = 0; tap < 3; ++tap)
-          tma_load_2d(w1 + (3 + tap) * 2048, &tm_b8, &s.w_full, 0, tap * a.cout_p);
+          tma_load_2d(w1 + (3 + 2 - tap) * 2048, &tm_b8, &s.w_full, 0, tap * a.cout_p);
       // Stage slot of pair i (i = -2 .. 256) is 16*(i+2): its four samples x[4t .. 4t+3].  An item spans at
       // most two reads (a read has more pairs than an item); pairs with 4t >= ld_x are not loaded (they lie
       // beyond every valid length and are masked by cvt1).
       const int t_max = static_cast<int>(a.ld_x >> 2);        // pairs per read that exist in x
-      F2Iter iter(flags0, n_items);
+      F2Iter iter(flags_l, n_items);
       int k = 0;
       for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
         const int st = k % kF2XStages;
@@ -1007,8 +1020,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       const uint32_t w1_addr = smem_u32(w1), b0_addr = smem_u32(b0);
       const uint32_t a0_addr = smem_u32(a0_ring), a1_addr = smem_u32(a1_ring);
       const uint32_t idesc0 = umma_idesc_f16(kBlockM, kF2N0);
+      const uint32_t idesc64 = umma_idesc_f16(kBlockM, 64);
       const uint64_t db0 = sw_desc<true>(b0_addr);
-      F2Iter iter(flags0, n_items);
+      F2Iter iter(flags_l, n_items);
       int k0 = 0;                       // items whose layer 0 has been issued
       auto issue_layer0 = [&]() {
         const int st = k0 & 1;
@@ -1041,35 +1055,40 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         for (int sub = 0; sub < 2; ++sub) {
           mbar_wait(&s.d1_empty[st][sub], ((k1 >> 1) & 1) ^ 1);
           tc_fence_after();
+        }
+        // even position 2j: w0*O[j-1] + w1*E[j] + w2*O[j];  odd position 2j+1: w0*E[j] + w1*O[j] + w2*E[j+1]
+        // (tile rows: E[j] = E row j, O[j] = O row j + 1; weight slot of tap t = 2 - t).
+        // Consecutive MMAs go to DIFFERENT accumulators (sub-tile x parity, round-robin): back-to-back
+        // MMAs into the same TMEM tile serialise on the accumulator (~80 cycles each at N = 32).
+        auto issue_group = [&](uint32_t a_tiles, uint32_t w_set, bool f8, bool first) {
 #pragma unroll
-          for (int pe = 0; pe < 2; ++pe) {
-            const uint32_t d = tmem_base + st * 128 + (2 * sub + pe) * 32;
+          for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
-            for (int tap = 0; tap < 3; ++tap) {
-              // even position: O[j-1], E[j], O[j];  odd position: E[j], O[j], E[j+1]
-              const int par = (pe == 0) ? ((tap == 1) ? 0 : 1) : ((tap == 1) ? 1 : 0);
-              const int shift = (pe == 0) ? ((tap == 2) ? 1 : 0) : ((tap == 0) ? 0 : 1);
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t db = sw_desc<true>(w_set + (2 - tap) * 2048) + 2 * k;
 #pragma unroll
-              for (int wp = 0; wp < WPLANES; ++wp) {
-                const uint64_t db = sw_desc<true>(w1_addr + (wp * 3 + tap) * 2048);
+              for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                for (int ap = 0; ap < ((wp == 0 && !F8) ? PLANES : 1); ++ap) {
-                  const uint64_t da =
-                      sw_desc<true>(a1s + (ap * 2 + par) * kF2A1Tile + (sub * 128 + shift) * 64);
-#pragma unroll
-                  for (int k = 0; k < 2; ++k)
-                    umma_f16(d, da + 2 * k, db + 2 * k, a.idesc, (tap | wp | ap | k) != 0);
+                for (int pe = 0; pe < 2; ++pe) {
+                  const int par = (pe == 0) ? ((tap == 1) ? 0 : 1) : ((tap == 1) ? 1 : 0);
+                  const int shift = (pe == 0) ? ((tap == 2) ? 1 : 0) : ((tap == 0) ? 0 : 1);
+                  const uint64_t da = sw_desc<true>(a_tiles + par * kF2A1Tile + (sub * 128 + shift) * 64) + 2 * k;
+                  const uint32_t d = tmem_base + st * 128 + (2 * sub + pe) * 32;
+                  if ((RISER_DBG & 1) && !(first && tap == 0 && k == 0)) continue;
+                  if (f8) umma_f8(d, da, db, a.idesc, 1);
+                  else umma_f16(d, da, db, a.idesc, !(first && tap == 0 && k == 0));
                 }
-              }
-              if (F8) {   // correction pass: [a8 | lo8] x [W_lo | W_hi * 2^-9], 64 e4m3 per row = 2 k-steps
-                const uint64_t db = sw_desc<true>(w1_addr + (3 + tap) * 2048);
-                const uint64_t da = sw_desc<true>(a1s + (2 + par) * kF2A1Tile + (sub * 128 + shift) * 64);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) umma_f8(d, da + 2 * k, db + 2 * k, a.idesc, 1);
               }
             }
           }
-        }
+        };
+#pragma unroll
+        for (int wp = 0; wp < WPLANES; ++wp)
+#pragma unroll
+          for (int ap = 0; ap < ((wp == 0 && !F8) ? PLANES : 1); ++ap)
+            issue_group(a1s + ap * 2 * kF2A1Tile, w1_addr + wp * 3 * 2048, false, wp == 0 && ap == 0);
+        if (F8)   // correction pass: [a8 | lo8] x [W_lo | W_hi * 2^-9], 64 e4m3 per row = 2 k-steps
+          issue_group(a1s + 2 * kF2A1Tile, w1_addr + 3 * 2048, true, false);
         umma_commit(&s.a1_empty[st]);
         umma_commit(&s.d1_full[st]);
         ++k1;
@@ -1080,7 +1099,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     // ===================== cvt1: signal -> layer-0 A rows =====================
     const int ct = (warp - 2) * 32 + lane;      // 0..63
     const __half2 one2 = __floats2half2_rn(1.f, 1.f);
-    F2Iter iter(flags0, n_items);
+    F2Iter iter(flags_l, n_items);
     int k = 0;
     for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
       const int st = k & 1;
@@ -1090,7 +1109,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       unsigned char* tile = a0_ring + st * kF2A0Tile;
       const float* xs = reinterpret_cast<const float*>(x_ring + xst * kF2XStage) + 8;   // xs[4*i + e]
       const long long u0 = static_cast<long long>(a.super0 + item) * kF2Pairs;
-      for (int i = ct - 1; i <= 255; i += kF2CvtThreads) {
+      for (int i = ct - 1; i <= 255 && !(RISER_DBG & 32); i += kF2CvtThreads) {
         const long long u = u0 + i;
         const bool inb = (u >= 0 && u < n_pairs);
         const uint32_t uu = inb ? static_cast<uint32_t>(u) : 0u;
@@ -1151,7 +1170,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     // ===================== mid-epilogue: layer-0 accumulators -> layer-1 A tiles =====================
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;                      // 0: E sub-tiles, 1: O sub-tiles
-    F2Iter iter(flags0, n_items);
+    F2Iter iter(flags_l, n_items);
     int k = 0;
     for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
       const int st = k & 1;
@@ -1163,16 +1182,32 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       for (int sub = 0; sub < 2; ++sub) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + kF2D0Col + (h * 2 + sub) * kF2N0;
         uint32_t e0[16], e1[8], o0[16], o1[8];
+        if (RISER_DBG & 4) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) e0[j] = o0[j] = 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e1[j] = o1[j] = 0u;
+        } else {
         tmem_ld_32x16(taddr, e0);
-        tmem_ld_32x8(taddr + 16, e1);
         tmem_ld_32x16(taddr + 24, o0);
-        tmem_ld_32x8(taddr + 40, o1);
+        }
+        if (RISER_DBG & 4) {
+        } else if (a.cout0 > 20) {        // TMEM reads are 64 B/clk per SM: do not fetch the zero columns
+          tmem_ld_32x8(taddr + 16, e1);
+          tmem_ld_32x8(taddr + 40, o1);
+        } else {
+#pragma unroll
+          for (int j = 4; j < 8; ++j) e1[j] = o1[j] = 0u;
+          tmem_ld_32x4(taddr + 16, e1);
+          tmem_ld_32x4(taddr + 40, o1);
+        }
         tmem_ld_wait();
         if (sub == 1) {          // both sub-tiles are in registers: layer 0 of the next item may overwrite them
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s.d0_empty[h]);
         }
+        if (RISER_DBG & 16) continue;
         const int row = sub * 128 + 32 * q + lane;
         unsigned char* rp = tile_hi + row * 64;
         const int sw = (row >> 1) & 3;
@@ -1232,9 +1267,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     const int q = warp & 3;
     const int sub = (warp - 12) >> 2;
     const int row_elems = a.cout_p * a.out_planes;
-    const int lo_off = (a.out_planes == 2 && !F8) ? a.cout_p : 0;
+    const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
     const float inv_scale = a.w_inv_scale;
-    F2Iter iter(flags0, n_items);
+    F2Iter iter(flags_l, n_items);
     int k = 0;
     for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
       const int st = k & 1;
@@ -1253,15 +1288,20 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
 #pragma unroll
       for (int c16 = 0; c16 < 2; ++c16) {
         uint32_t ve[16], vo[16];
-        tmem_ld_32x16(taddr + c16 * 16, ve);
-        tmem_ld_32x16(taddr + 32 + c16 * 16, vo);
+        if (RISER_DBG & 8) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ve[j] = vo[j] = 0u;
+        } else {
+          tmem_ld_32x16(taddr + c16 * 16, ve);
+          tmem_ld_32x16(taddr + 32 + c16 * 16, vo);
+        }
         tmem_ld_wait();
         if (c16 == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s.d1_empty[st][sub]);
         }
-        if (writable) {
+        if (writable && !((RISER_DBG & 2) && a.Lp_out > 0)) {
           float r[16];
           if (valid) {
 #pragma unroll
@@ -1295,7 +1335,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
             ol[0] = *reinterpret_cast<const uint4*>(lv);
             ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
           }
-          if (F8)
+          if (a.out_f8)
             store_f8_planes<16>(r, hv, reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c16 * 16, a.cout_p);
         }
         __syncwarp();
@@ -1535,6 +1575,7 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   m->f8 = (precision == RISER_PREC_F16_F8) ? 1 : 0;
   m->passes = (precision == RISER_PREC_F16 || m->f8) ? 1 : 2;  // fp16 weight planes (hi [, lo])
   m->act_planes = (precision == RISER_PREC_F16_X3 || m->f8) ? 2 : 1;   // activation planes (hi [, lo])
+  m->f8_from = std::max(1, env_int("RISER_F8_FROM", 6));
   m->device = device;
   cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
   int cin = 1, cin_p = 1;
@@ -1543,6 +1584,8 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
     L.cin = cin;
     L.cout = channels[i];
     L.cin_p = cin_p;
+    L.f8 = (m->f8 && i >= m->f8_from) ? 1 : 0;
+    L.passes = m->f8 ? (L.f8 ? 1 : 2) : m->passes;
     L.n_tile = (i == 0) ? round_up(L.cout, 16) : pick_n_tile(L.cout);
     L.cout_p = round_up(L.cout, L.n_tile);
     L.n_tiles = L.cout_p / L.n_tile;
@@ -1556,8 +1599,8 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
     } else {
       // [plane][tap][cout_p][cin_p]: tap-major so that one 2-D tensor map serves all taps
       const size_t per_pass = static_cast<size_t>(3) * L.cout_p * L.cin_p;
-      std::vector<__half> w(per_pass * m->passes, __float2half(0.f));
-      std::vector<uint8_t> w8(m->f8 ? 2 * per_pass : 0, 0);
+      std::vector<__half> w(per_pass * L.passes, __float2half(0.f));
+      std::vector<uint8_t> w8(L.f8 ? 2 * per_pass : 0, 0);
       const float* src = conv_w[i];   // [cout][cin][3]
       float wmax = 0.f;
       for (size_t k = 0; k < static_cast<size_t>(L.cout) * L.cin * 3; ++k) wmax = std::max(wmax, std::fabs(src[k]));
@@ -1576,14 +1619,14 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
             const __half hi = __float2half_rn(v);
             const size_t idx = (static_cast<size_t>(tap) * L.cout_p + co) * L.cin_p + ci;
             w[idx] = hi;
-            if (m->passes == 2) w[per_pass + idx] = __float2half_rn(v - __half2float(hi));
-            if (m->f8) {   // correction operands: [W_lo | W_hi * 2^-9] e4m3 (pair with a8 and lo8 * 2^9)
+            if (L.passes == 2) w[per_pass + idx] = __float2half_rn(v - __half2float(hi));
+            if (L.f8) {   // correction operands: [W_lo | W_hi * 2^-9] e4m3 (pair with a8 and lo8 * 2^9)
               const size_t i8 = (static_cast<size_t>(tap) * L.cout_p + co) * (2 * L.cin_p) + ci;
               w8[i8] = __nv_cvt_float_to_fp8(v - __half2float(hi), __NV_SATFINITE, __NV_E4M3);
               w8[i8 + L.cin_p] = __nv_cvt_float_to_fp8(v * (1.f / kF8LoScale), __NV_SATFINITE, __NV_E4M3);
             }
           }
-      if (m->f8) {
+      if (L.f8) {
         RISER_CUDA_TRY(cudaMalloc(&L.w8, w8.size()));
         RISER_CUDA_TRY(cudaMemcpy(L.w8, w8.data(), w8.size(), cudaMemcpyHostToDevice));
       }
@@ -1693,8 +1736,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const int k_elems = row_bytes / 2;
     int st = make_tmap(&lp.tm_a, p->ws + p->act_off[i], static_cast<uint64_t>(L.cin_p) * m->act_planes, rows_in,
                        a_box_rows, k32);
-    if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(m->passes) * 3 * L.cout_p, L.n_tile, k32);
-    if (!st && m->f8) {
+    if (!st) st = make_tmap(&lp.tm_b, L.w, L.cin_p, static_cast<uint64_t>(L.passes) * 3 * L.cout_p, L.n_tile, k32);
+    if (!st && L.f8) {
       st = make_tmap8(&lp.tm_a8, p->ws + p->act_off[i], 4ull * L.cin_p, 4ull * L.cin_p, rows_in, a_box_rows, k32);
       if (!st) st = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, L.n_tile, k32);
     } else {
@@ -1718,13 +1761,13 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.n_tile = L.n_tile;
     a.n_tiles = L.n_tiles;
     a.kb16 = (L.cin_p + k_elems - 1) / k_elems;
-    a.k_blocks = a.kb16 + (m->f8 ? (2 * L.cin_p + row_bytes - 1) / row_bytes : 0);
+    a.k_blocks = a.kb16 + (L.f8 ? (2 * L.cin_p + row_bytes - 1) / row_bytes : 0);
     a.k32 = k32 ? 1 : 0;
-    a.f8 = m->f8;
-    a.out_f8 = (m->f8 && !last) ? 1 : 0;
-    const int kplanes = m->f8 ? 1 : m->act_planes;     // activation tiles per K block
+    a.f8 = L.f8;
+    a.out_f8 = (!last && m->layer[i + 1].f8) ? 1 : 0;   // the epilogue writes the format the next layer reads
+    const int kplanes = L.f8 ? 1 : m->act_planes;      // activation tiles per K block
     a.planes = kplanes;
-    a.wplanes = m->passes;
+    a.wplanes = L.passes;
     a.out_fp32 = last ? 1 : 0;
     a.out_planes = last ? 1 : m->act_planes;
     a.idesc = umma_idesc_f16(kBlockM, L.n_tile);
@@ -1736,7 +1779,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     const size_t b_bytes = static_cast<size_t>(L.n_tile) * row_bytes;
     const size_t fixed = 1024 + sizeof(ConvSmem) + 64;
     const size_t avail = static_cast<size_t>(max_smem) - fixed;
-    const size_t w_all = static_cast<size_t>(m->passes) * 3 * a.k_blocks * b_bytes;
+    const size_t w_all = static_cast<size_t>(L.passes) * 3 * a.k_blocks * b_bytes;
     const size_t a_group1 = static_cast<size_t>(kplanes) * 136 * row_bytes;
     if (allow_resident && L.n_tiles == 1 && w_all + 2 * a_group1 <= avail) {
       // resident weights; as many 128-row sub-tiles per work item as leave >= 2 accumulator
@@ -1801,7 +1844,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b0 = m->layer[0].bias;
       a.cout0 = m->layer[0].cout;
       lp.rows_per_super = 2 * kF2Pairs;
-      lp.smem = fused01_smem(m->act_planes, m->f8 ? 2 : m->passes);
+      lp.smem = fused01_smem(m->act_planes, L.f8 ? 2 : L.passes);
       a.planes = m->act_planes;     // fused01_kernel's own modes (see pick_fused01)
     }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
@@ -1886,7 +1929,7 @@ int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32
   __half* out = reinterpret_cast<__half*>(p->ws + p->act_off[1]) +
                 static_cast<int64_t>(b0) * p->Lp[1] * L.cout_p * m->act_planes;
   layer0_kernel<<<grid, 256, 0, st>>>(x + static_cast<int64_t>(b0) * ld_x, ld_x, len + b0, L.w0, L.bias, out, nb,
-                                      p->Lp[1], L.cout, L.cout_p, m->act_planes, m->f8);
+                                      p->Lp[1], L.cout, L.cout_p, m->act_planes, m->layer[1].f8);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
@@ -1911,6 +1954,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
   a.n_supers = static_cast<int>((row1 + rows_per_super - 1) / rows_per_super) - a.super0;
   const int grid = std::min(a.n_supers * a.n_tiles, p->model->sm_count);
   if (fused2) {
+    if ((a.n_supers + grid - 1) / grid > kF2MaxLocalItems) a.flags = nullptr;   // (every item treated as active)
     RISER_REQUIRE((ld_x & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                   "riser_forward: x must be 16-byte aligned with ld_x a multiple of 4 (bulk copies of the signal)");
     pick_fused01(a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(

@@ -18,7 +18,7 @@ PREC_F16 = 0       # one tcgen05 pass, fp16 weights
 PREC_F16_W2 = 1    # two passes, weights split hi + lo (exact to ~22 bits)
 PREC_F16_X3 = 2    # three passes, weights and activations split hi + lo: fp32-class
 PREC_F16_F8 = 3    # fp16 pass + one e4m3 pass carrying both hi/lo correction terms (2 pass-equivalents)
-DEFAULT_PRECISION = PREC_F16_X3
+DEFAULT_PRECISION = PREC_F16_F8
 MIN_LENGTH = 4096  # riser/preprocess.py:8 -- 12 stride-2 pools
 DEFAULT_CHUNK = 0    # 0 = whole batch in one plan (the plan chunks the early layers itself)
 

@@ -50,9 +50,14 @@ def oracle_layers(state, x):
 
 @pytest.mark.parametrize("fuse,precision", [(0, PREC_F16), (0, PREC_F16_W2), (0, PREC_F16_X3), (1, PREC_F16),
                                             (1, PREC_F16_W2), (1, PREC_F16_X3), (2, PREC_F16), (2, PREC_F16_W2),
-                                            (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8)])
+                                            (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8),
+                                            (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
+    f8_from = 6                      # F16_F8: first layer that runs the e4m3 correction pass (default 6)
+    if isinstance(precision, tuple):
+        precision, f8_from = precision
+        monkeypatch.setenv("RISER_F8_FROM", str(f8_from))
     rng = np.random.default_rng(0)
     lengths = [4096, 5001, 7108, 12048, 12047, 8615, 4097]
     normed = [pp.mad_normalise(synth.body(rng, n)) for n in lengths]
@@ -68,7 +73,7 @@ def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     for b, v in enumerate(normed):
         want = oracle_layers(state, torch.from_numpy(np.asarray(v, dtype=np.float64)).float())
         for i in range(2 if plan.fused_layer0 else 1, 13):
-            planes = {PREC_F16_X3: 2, PREC_F16_F8: 3}.get(precision, 1)
+            planes = {PREC_F16_X3: 2, PREC_F16_F8: 3 if i >= f8_from else 2}.get(precision, 1)
             act = plan.activation(i, 12, planes=planes)[b].float().cpu()
             w = want[i - 1].T                                  # [L_i, C]
             L = w.shape[0]
