@@ -186,6 +186,11 @@ int riser_plan_fused_layer0(const riser_plan* p);
 int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
                           int* channels_padded, int* channels, int* n_tile);
 
+/* 1 when layer i's input buffer uses the even / odd plane layout: all even rows of every
+ * read (row = b * rows_per_read / 2 + t / 2) followed by all odd rows, instead of the flat
+ * [B * rows_per_read] order.  Same size, same row format.                            */
+int riser_plan_layer_eo(const riser_plan* p, int i);
+
 /* Replaces the decision rule of riser/control.py:75-82 for M models:
  * probs [M, B, 2]; len [B] = post-trim window length, 0 = read was skipped
  * (control.py:50,56) -> RISER_SKIPPED.  Strict '>' against thr in fp32.        */

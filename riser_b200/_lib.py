@@ -37,6 +37,7 @@ SIGNATURES = {
     "riser_forward_launches": (c_int, [c_void_p]),
     "riser_plan_fused_layer0": (c_int, [c_void_p]),
     "riser_plan_layer_info": (c_int, [c_void_p, c_int, P(c_i64), P(c_int), P(c_int), P(c_int), P(c_int)]),
+    "riser_plan_layer_eo": (c_int, [c_void_p, c_int]),
     "riser_conv1d_cl": (c_int, [c_void_p] * 7 + [c_int] * 9 + [c_void_p]),
     "riser_maxpool1d_cl": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "riser_gap_linear_softmax": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),

@@ -29,6 +29,13 @@
 namespace riser {
 namespace {
 
+// Timing experiments only (results are wrong when set): fused01_kernel 1 = one MMA per layer-1 accumulator,
+// 2 = no global stores, 4 / 8 = mid-epilogue / epilogue skip their TMEM loads, 16 = mid-epilogue idle,
+// 32 = cvt1 idle; conv_tc_kernel 64 = one MMA per accumulator, 128 = epilogue idle after its TMEM loads,
+// 256 = epilogue skips its TMEM loads.
+#ifndef RISER_DBG
+#define RISER_DBG 0
+#endif
 constexpr int kMaxLayers = 16;
 constexpr int kBlockM = 128;          // rows per tile (UMMA M)
 constexpr int kBlockK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
@@ -108,6 +115,8 @@ struct ConvArgs {
   int kb16;               // K blocks of the fp16 pass (== k_blocks unless f8: then k_blocks - kb16 e4m3 blocks follow)
   int f8;                 // 1 = RISER_PREC_F16_F8: input rows are [hi fp16 | a8 | lo8], see riser_model_create
   int out_f8;             // output rows in that format
+  int out_eo;             // output rows in the even / odd plane layout of conv_eo_kernel (else flat [B * Lp_out])
+  int n_pairs_out, half_lp_out;
   // fused layer 0 (layer 1 only): A tiles are computed in-kernel from the normalised signal
   const float* x;
   long long ld_x;
@@ -128,7 +137,8 @@ struct ActivityArgs {
 };
 
 struct LayerPlan {
-  CUtensorMap tm_a, tm_b, tm_a8, tm_b8;
+  CUtensorMap tm_a, tm_b, tm_a8, tm_b8;   // (EO layers: tm_a = E plane, tm_a8 = O plane)
+  int eo = 0;                             // input in the even / odd plane layout -> conv_eo_kernel
   ConvArgs args;
   int n_supers_total = 0;
   int rows_per_super = 0;   // flat input rows one work item covers (ms * 128; 510 for the fused layers 0+1)
@@ -333,6 +343,48 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
     }
     if (f8_row) store_f8_planes<8>(r, h, f8_row + c, f8_stride);
   }
+}
+
+// Epilogue for 16 output channels of ONE pooled row held by this lane: ve / vo are the accumulators of the
+// even and the odd conv position (same TMEM lane).  max-pool, scale + bias, ReLU, then fp16 hi (+ lo plane,
+// or the e4m3 pair of F16_F8) straight into the next layer's row.
+__device__ __forceinline__ void epilogue_row16(const uint32_t (&ve)[16], const uint32_t (&vo)[16], const float* bias16,
+                                               bool valid, float inv_scale, __half* ohi, int lo_off, uint8_t* f8,
+                                               int f8_stride) {
+  float r[16];
+  if (valid) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias16 + c4 * 4);
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c4 * 4 + e;
+        r[c] = fmaxf(fmaf(fmaxf(__uint_as_float(ve[c]), __uint_as_float(vo[c])), inv_scale, bv[e]), 0.f);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) r[c] = 0.f;
+  }
+  __half2 hv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
+  uint4* oh = reinterpret_cast<uint4*>(ohi);
+  oh[0] = *reinterpret_cast<const uint4*>(hv);
+  oh[1] = *reinterpret_cast<const uint4*>(hv + 4);
+  if (lo_off) {
+    __half2 lv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 back = __half22float2(hv[c]);
+      lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
+    }
+    uint4* ol = reinterpret_cast<uint4*>(ohi + lo_off);
+    ol[0] = *reinterpret_cast<const uint4*>(lv);
+    ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
+  }
+  if (f8) store_f8_planes<16>(r, hv, f8, f8_stride);
 }
 
 // Descriptor for a K-major swizzled tile at shared address `addr` (< 256 KB): rows of 128 bytes
@@ -558,7 +610,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                             : sw_desc<K32>(a_addr + (ms * PLANES + ap) * kATile + tap * kRowBytes);
 #pragma unroll
                   for (int k = 0; k < kKElems / 16; ++k)
-                    if (k < nk) {
+                    if (k < nk && !((RISER_DBG & 64) && (kb | tap | wp | ap | k) != 0)) {
                       if (is8)
                         umma_f8(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
                       else
@@ -715,7 +767,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int tp = static_cast<int>(pidx) - b * a.half_lp;
           valid[ms] = tp < (__ldg(a.len0 + b) >> a.shift);
           writable[ms] = tp < a.Lp_out;
-          out_row[ms] = static_cast<int64_t>(b) * a.Lp_out + tp;
+          out_row[ms] = a.out_eo ? static_cast<int64_t>(tp & 1) * a.n_pairs_out + static_cast<int64_t>(b) * a.half_lp_out + (tp >> 1)
+                                 : static_cast<int64_t>(b) * a.Lp_out + tp;
         }
       }
       mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
@@ -732,8 +785,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (; u < (ms + 1) * n_chunks; u += a.epi_sets) {
           const int c = u - ms * n_chunks;
           uint32_t v[16];
-          tmem_ld_32x16(t_addr + c * 16, v);
+          if (RISER_DBG & 256) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          } else {
+            tmem_ld_32x16(t_addr + c * 16, v);
+          }
           tmem_ld_wait();
+          if ((RISER_DBG & 128) && a.Lp_out > 0) continue;
           uint8_t* f8_row = nullptr;
           if (a.out_f8)
             f8_row = static_cast<uint8_t*>(a.out) + out_row[ms] * row_elems * 2 + 2 * a.cout_p + n0;
@@ -827,9 +886,6 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
 //   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
 //   warps 4..11   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
 //   warps 12..19  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
-#ifndef RISER_DBG
-#define RISER_DBG 0      // timing experiments only (wrong results): 1 = one MMA per layer-1 accumulator, 2 = no global
-#endif                   // stores, 4 = mid-epilogue skips its TMEM loads, 8 = epilogue skips its TMEM loads
 constexpr int kF2Pairs = 255;
 constexpr int kF2Threads = 640;
 constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shifted taps of row 255 touch
@@ -1281,7 +1337,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       const int tp = static_cast<int>(uu) - b * a.half_lp;
       const bool valid = ok && tp < (__ldg(a.len0 + b) >> a.shift);
       const bool writable = ok && tp < a.Lp_out;
-      __half* orow = static_cast<__half*>(a.out) + (static_cast<int64_t>(b) * a.Lp_out + tp) * row_elems;
+      const int64_t out_row = a.out_eo ? static_cast<int64_t>(tp & 1) * a.n_pairs_out + static_cast<int64_t>(b) * a.half_lp_out + (tp >> 1)
+                                       : static_cast<int64_t>(b) * a.Lp_out + tp;
+      __half* orow = static_cast<__half*>(a.out) + out_row * row_elems;
       mbar_wait_relaxed(&s.d1_full[st], (k >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + st * 128 + 2 * sub * 32;
@@ -1361,6 +1419,246 @@ FusedKernelFn pick_fused01(int mode) {
 size_t fused01_smem(int planes, int wplanes) {
   return 1024 + static_cast<size_t>(wplanes) * 3 * 32 * 64 + kF2N0 * 64 + 2 * kF2A0Tile +
          2 * static_cast<size_t>(planes) * 2 * kF2A1Tile + kF2XStages * kF2XStage + sizeof(F2Smem) + 64;
+}
+
+// ------------------------------------------------------------------------------------
+// Narrow layers with the even / odd row layout ("EO", layers 2..4 of the shipped network).
+//
+// For N <= 128 a tcgen05.mma is paced by its A-operand fetch from shared memory (~64 cycles per
+// M = 128, K = 16 instruction whatever N is) and the epilogue by instruction issue, so what counts
+// is the NUMBER of MMAs and of epilogue instructions per output.  With the input stored as an
+// E plane (rows 2j of every read, flat pair index u = b * half_lp + j) followed by an O plane
+// (rows 2j + 1), the conv at position 2j is  w0*O[j-1] + w1*E[j] + w2*O[j]  and at 2j + 1
+// w0*E[j] + w1*O[j] + w2*E[j+1]; grouped by A rows
+//     E[j]   x [w1; w0] -> (even | odd)        O[j]   x [w2; w1] -> (even | odd)       (N = 2n)
+//     O[j-1] x  w0      ->  even                E[j+1] x  w2      ->  odd               (N = n)
+// i.e. 4 MMAs instead of 6 per K step, the two positions of a max-pool pair land in the same TMEM
+// lane (pooling = in-lane max, no shuffles), and a lane owns a whole output row.  Tiles are flat
+// slices of the pair index; the rows that separate reads are zero as in the flat layout (O[-1] of a
+// read is the previous read's last odd row, which lies beyond every valid length).
+// Weights are resident ([plane][K block][tap slot 2 - tap][n_tile rows x 64 B]); 32-channel K blocks.
+constexpr uint32_t kEoTile = 136 * 64;      // 128 rows + 1 halo row (+ 7: TMA box of 136 rows), 64-byte rows
+
+template <int MS, int PLANES, int WPLANES>
+__global__ void __launch_bounds__(64 + 128 * kMaxEpiSets, 1)
+conv_eo_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_o,
+               const __grid_constant__ CUtensorMap tm_b, const ConvArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  constexpr uint32_t kGroup = MS * PLANES * 2 * kEoTile;           // A tiles of one K block: [sub][plane][E, O]
+  const uint32_t b_bytes = a.n_tile * 64;
+  unsigned char* a_ring = base;
+  unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kGroup;
+  const size_t b_region_bytes = static_cast<size_t>(WPLANES) * a.k_blocks * 3 * b_bytes;
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + b_region_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_items = a.n_supers;
+  const int acc2 = a.acc_cols;                 // TMEM columns of one sub-tile: [even n | odd n], rounded to 32
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_e);
+    tma_prefetch_desc(&tm_o);
+    tma_prefetch_desc(&tm_b);
+    for (int i = 0; i < a.a_stages; ++i) {
+      mbar_init(&s.a_full[i], 1);
+      mbar_init(&s.a_empty[i], 1);
+    }
+    mbar_init(&s.w_full, 1);
+    for (int i = 0; i < a.acc_stages; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      for (int ms = 0; ms < MS; ++ms) mbar_init(&s.tmem_empty[i][ms], 4 * a.epi_sets);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s.tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&s.w_full, static_cast<uint32_t>(b_region_bytes));
+      for (int wp = 0; wp < WPLANES; ++wp)
+        for (int kb = 0; kb < a.k_blocks; ++kb)
+          for (int tap = 0; tap < 3; ++tap)
+            tma_load_2d(b_region + static_cast<size_t>((wp * a.k_blocks + kb) * 3 + 2 - tap) * b_bytes, &tm_b,
+                        &s.w_full, kb * 32, (wp * 3 + tap) * a.cout_p);
+      int sa = 0;
+      uint32_t pa = 0;
+      ItemCursor cur(blockIdx.x, gridDim.x, 1, a.super0);
+      ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+        if (!fl.take(cur, item + gridDim.x < n_items)) continue;
+        const int u0 = cur.super * (MS * kBlockM);
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&s.a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&s.a_full[sa], MS * PLANES * 2 * kEoTile);
+          unsigned char* dst = a_ring + static_cast<size_t>(sa) * kGroup;
+#pragma unroll
+          for (int ms = 0; ms < MS; ++ms)
+#pragma unroll
+            for (int ap = 0; ap < PLANES; ++ap) {
+              unsigned char* t = dst + (ms * PLANES + ap) * 2 * kEoTile;
+              tma_load_2d(t, &tm_e, &s.a_full[sa], ap * a.cin_p + kb * 32, u0 + ms * kBlockM);              // E[j ..]
+              tma_load_2d(t + kEoTile, &tm_o, &s.a_full[sa], ap * a.cin_p + kb * 32, u0 + ms * kBlockM - 1);  // O[j-1 ..]
+            }
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(&s.w_full, 0);
+      tc_fence_after();
+      int sa = 0, stage = 0;
+      uint32_t pa = 0, acc_phase = 0;
+      const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
+      const int nk_last = (a.cin_p - (a.k_blocks - 1) * 32) / 16;
+      const uint32_t idesc1 = a.idesc;                                  // N = n_tile
+      const uint32_t idesc2 = umma_idesc_f16(kBlockM, 2 * a.n_tile);    // N = 2 n_tile: (even | odd)
+      ItemCursor cur(blockIdx.x, gridDim.x, 1, a.super0);
+      ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+        if (!fl.take(cur, item + gridDim.x < n_items)) continue;
+        const uint32_t d_base = tmem_base + stage * (MS * acc2);
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          const int nk = (kb == a.k_blocks - 1) ? nk_last : 2;
+          mbar_wait(&s.a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_addr = a_ring_addr + sa * kGroup;
+#pragma unroll
+          for (int wp = 0; wp < WPLANES; ++wp) {
+            const uint32_t w_set = b_region_addr + ((wp * a.k_blocks + kb) * 3) * b_bytes;   // slots: w2, w1, w0
+#pragma unroll
+            for (int ms = 0; ms < MS; ++ms) {
+              if (kb == 0 && wp == 0) {      // first touch of this accumulator: wait until drained
+                mbar_wait(&s.tmem_empty[stage][ms], acc_phase ^ 1);
+                tc_fence_after();
+              }
+              const uint32_t d_even = d_base + ms * acc2, d_odd = d_even + a.n_tile;
+#pragma unroll
+              for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {      // W_lo only meets the hi plane
+                const uint32_t e_rows = a_addr + (ms * PLANES + ap) * 2 * kEoTile, o_rows = e_rows + kEoTile;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  if (k < nk) {
+                    const uint64_t w21 = sw_desc<true>(w_set) + 2 * k;
+                    const uint64_t w10 = sw_desc<true>(w_set + b_bytes) + 2 * k;
+                    const uint64_t w0 = sw_desc<true>(w_set + 2 * b_bytes) + 2 * k;
+                    umma_f16(d_even, sw_desc<true>(e_rows) + 2 * k, w10, idesc2, (kb | wp | ap | k) != 0);   // E[j]
+                    umma_f16(d_even, sw_desc<true>(o_rows + 64) + 2 * k, w21, idesc2, 1);                    // O[j]
+                    umma_f16(d_even, sw_desc<true>(o_rows) + 2 * k, w0, idesc1, 1);                          // O[j-1]
+                    umma_f16(d_odd, sw_desc<true>(e_rows + 64) + 2 * k, w21, idesc1, 1);                     // E[j+1] x w2
+                  }
+              }
+            }
+          }
+          umma_commit(&s.a_empty[sa]);
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit(&s.tmem_full[stage]);
+        if (++stage == a.acc_stages) {
+          stage = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 2 + 4 * a.epi_sets) {
+    // ===================== epilogue: one output row per lane =====================
+    const int q = warp & 3;
+    const int eset = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    const int epi_threads = 128 * a.epi_sets;
+    const int row_elems = a.cout_p * a.out_planes;
+    const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
+    const int n_chunks = a.n_tile >> 4;
+    const int n_pairs = a.rows_in >> 1;
+    for (int i = et; i < a.n_tile; i += epi_threads) s.bias[0][i] = a.bias[i];
+    asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+    int stage = 0;
+    uint32_t acc_phase = 0;
+    ItemCursor cur(blockIdx.x, gridDim.x, 1, a.super0);
+    ItemFlags fl(a.flags, cur.super, blockIdx.x < n_items);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, cur.next()) {
+      if (!fl.take(cur, item + gridDim.x < n_items)) continue;
+      const int u0 = cur.super * (MS * kBlockM);
+      bool valid[MS], writable[MS];
+      int64_t out_row[MS];
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        valid[ms] = writable[ms] = false;
+        out_row[ms] = 0;
+        const int u = u0 + ms * kBlockM + 32 * q + lane;
+        if (u < n_pairs) {
+          const int b = static_cast<int>((static_cast<unsigned long long>(static_cast<uint32_t>(u)) * a.pair_magic) >> 40);
+          const int tp = u - b * a.half_lp;
+          valid[ms] = tp < (__ldg(a.len0 + b) >> a.shift);
+          writable[ms] = tp < a.Lp_out;
+          out_row[ms] = a.out_eo ? static_cast<int64_t>(tp & 1) * a.n_pairs_out + static_cast<int64_t>(b) * a.half_lp_out + (tp >> 1)
+                                 : static_cast<int64_t>(b) * a.Lp_out + tp;
+        }
+      }
+      mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
+      tc_fence_after();
+      int uw = eset;       // work units = (sub-tile, 16-column chunk), dealt round-robin to the epilogue sets
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        __half* orow = static_cast<__half*>(a.out) + out_row[ms] * row_elems;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (stage * MS + ms) * acc2;
+        for (; uw < (ms + 1) * n_chunks; uw += a.epi_sets) {
+          const int c = uw - ms * n_chunks;
+          uint32_t ve[16], vo[16];
+          tmem_ld_32x16(t_addr + c * 16, ve);
+          tmem_ld_32x16(t_addr + a.n_tile + c * 16, vo);
+          tmem_ld_wait();
+          if (writable[ms])
+            epilogue_row16(ve, vo, s.bias[0] + c * 16, valid[ms], a.w_inv_scale, orow + c * 16, lo_off,
+                           a.out_f8 ? reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c * 16 : nullptr, a.cout_p);
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.tmem_empty[stage][ms]);
+      }
+      if (++stage == a.acc_stages) {
+        stage = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*EoKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+EoKernelFn pick_conv_eo(int ms, int planes, int wplanes) {
+  if (ms == 2) {
+    if (planes == 1 && wplanes == 1) return conv_eo_kernel<2, 1, 1>;
+    if (planes == 1 && wplanes == 2) return conv_eo_kernel<2, 1, 2>;
+    return conv_eo_kernel<2, 2, 2>;
+  }
+  if (planes == 1 && wplanes == 1) return conv_eo_kernel<1, 1, 1>;
+  if (planes == 1 && wplanes == 2) return conv_eo_kernel<1, 1, 2>;
+  return conv_eo_kernel<1, 2, 2>;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1720,6 +2018,17 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     p->n_chunked = std::max(0, std::min(m->n_layers, env_int("RISER_CHUNKED_LAYERS", n_chunked)));
   }
 
+  // Even / odd plane layout (conv_eo_kernel) for the narrow resident-weight layers after layer 1
+  if (env_int("RISER_EO", 1))
+    for (int i = 2; i < m->n_layers - 1; ++i) {
+      const LayerPack& L = m->layer[i];
+      const size_t w_all = static_cast<size_t>(L.passes) * ((L.cin_p + 31) / 32) * 3 * L.n_tile * 64;
+      const size_t group1 = static_cast<size_t>(m->act_planes) * 2 * kEoTile;
+      if (!L.f8 && L.cin_p <= 80 && L.n_tiles == 1 && 2 * L.n_tile <= kMaxNTile &&
+          w_all + 2 * group1 + 1024 + sizeof(ConvSmem) + 64 <= static_cast<size_t>(max_smem) && i <= env_int("RISER_EO_LAST", 4))
+        p->layer[i].eo = 1;
+    }
+
   for (int i = 1; i < m->n_layers; ++i) {
     const LayerPack& L = m->layer[i];
     LayerPlan& lp = p->layer[i];
@@ -1765,6 +2074,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     a.k32 = k32 ? 1 : 0;
     a.f8 = L.f8;
     a.out_f8 = (!last && m->layer[i + 1].f8) ? 1 : 0;   // the epilogue writes the format the next layer reads
+    a.out_eo = (!last && p->layer[i + 1].eo) ? 1 : 0;    // ... and the row layout it reads
+    a.n_pairs_out = B * p->Lp[i + 1] / 2;
+    a.half_lp_out = p->Lp[i + 1] / 2;
     const int kplanes = L.f8 ? 1 : m->act_planes;      // activation tiles per K block
     a.planes = kplanes;
     a.wplanes = L.passes;
@@ -1847,6 +2159,27 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fused01_smem(m->act_planes, L.f8 ? 2 : L.passes);
       a.planes = m->act_planes;     // fused01_kernel's own modes (see pick_fused01)
     }
+    if (lp.eo) {
+      // conv_eo_kernel: E plane = rows [0, n_pairs), O plane = rows [n_pairs, 2 n_pairs) of the same buffer
+      const uint64_t n_pairs = static_cast<uint64_t>(rows_in) / 2;
+      const uint64_t pitch = static_cast<uint64_t>(L.cin_p) * m->act_planes;     // fp16 elements per row
+      int st2 = make_tmap(&lp.tm_a, p->ws + p->act_off[i], pitch, n_pairs, 136, true);
+      if (!st2) st2 = make_tmap(&lp.tm_a8, p->ws + p->act_off[i] + n_pairs * pitch * 2, pitch, n_pairs, 136, true);
+      if (st2) {
+        delete p;
+        return st2;
+      }
+      a.acc_cols = round_up(2 * L.n_tile, 32);
+      const size_t w_eo = static_cast<size_t>(L.passes) * a.k_blocks * 3 * b_bytes;
+      const size_t group1 = static_cast<size_t>(m->act_planes) * 2 * kEoTile;
+      a.ms = (2 * 2 * a.acc_cols <= kTmemCols && w_eo + 2 * 2 * group1 <= avail && env_int("RISER_EO_MS", 2) >= 2) ? 2 : 1;
+      a.resident = 1;
+      a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_eo) / (a.ms * group1)));
+      a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+      a.epi_sets = 4;
+      lp.smem = fixed + w_eo + static_cast<size_t>(a.a_stages) * a.ms * group1;
+      lp.rows_per_super = a.ms * 2 * kBlockM;
+    }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
   }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
@@ -1875,6 +2208,10 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
               reinterpret_cast<const void*>(pick_conv_kernel(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2, mode >= 1,
                                                              mode == 2, k32v)),
               cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  for (int ms = 1; ms <= 2; ++ms)
+    for (int pl = 0; pl < 3; ++pl)
+      RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_eo(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2)),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   for (int pl = 0; pl < 4; ++pl)
     RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl)),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1902,6 +2239,10 @@ extern "C" int riser_forward_launches(const riser_plan* p) {
 }
 
 extern "C" int riser_plan_fused_layer0(const riser_plan* p) { return p ? p->fuse_l0 : 0; }
+
+extern "C" int riser_plan_layer_eo(const riser_plan* p, int i) {
+  return (p && i >= 1 && i < p->model->n_layers) ? p->layer[i].eo : 0;
+}
 
 extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
                                      int* channels_padded, int* channels, int* n_tile) {
@@ -1959,6 +2300,11 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
                   "riser_forward: x must be 16-byte aligned with ld_x a multiple of 4 (bulk copies of the signal)");
     pick_fused01(a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(
         lp.tm_b, lp.tm_b8, a);
+    RISER_CUDA_TRY(cudaGetLastError());
+    return RISER_OK;
+  }
+  if (lp.eo) {
+    pick_conv_eo(a.ms, a.planes, a.wplanes)<<<grid, 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_a8, lp.tm_b, a);
     RISER_CUDA_TRY(cudaGetLastError());
     return RISER_OK;
   }

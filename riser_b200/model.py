@@ -50,13 +50,18 @@ class Plan:
         off, rows, cp, c, _ = self.layer_info(i)
         dt = torch.float32 if i == n_layers else torch.float16
         nbytes = self.B * rows * cp * (4 if i == n_layers else 2)
-        full = self.workspace[off:off + nbytes].view(dt).view(self.B, rows, cp)
+        full = self.workspace[off:off + nbytes].view(dt)
+        if i != n_layers and _lib.lib().riser_plan_layer_eo(self._handle, i):
+            # even / odd plane layout: [parity][b][t // 2] -> [b][t]
+            full = full.view(2, self.B, rows // 2, cp).permute(1, 2, 0, 3).reshape(self.B, rows, cp)
+        else:
+            full = full.view(self.B, rows, cp)
         if planes == 2 and i != n_layers:      # hi + lo planes side by side
             half = cp // 2
             return full[:, :, :c].float() + full[:, :, half:half + c].float()
         if planes == 3 and i != n_layers:      # F16_F8 rows: [hi fp16 | a8 e4m3 | lo8 e4m3 = (a - hi) * 2^9]
             half = cp // 2
-            raw = self.workspace[off:off + nbytes].view(self.B, rows, cp * 2)
+            raw = full.contiguous().view(torch.uint8).view(self.B, rows, cp * 2)
             lo8 = raw[:, :, 3 * half:3 * half + c].contiguous().view(torch.float8_e4m3fn).float()
             return full[:, :, :c].float() + lo8 / 512.0
         return full[:, :, :c]

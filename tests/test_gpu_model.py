@@ -51,11 +51,15 @@ def oracle_layers(state, x):
 @pytest.mark.parametrize("fuse,precision", [(0, PREC_F16), (0, PREC_F16_W2), (0, PREC_F16_X3), (1, PREC_F16),
                                             (1, PREC_F16_W2), (1, PREC_F16_X3), (2, PREC_F16), (2, PREC_F16_W2),
                                             (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8),
-                                            (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3))])
+                                            (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3)),
+                                            (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat"))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
     f8_from = 6                      # F16_F8: first layer that runs the e4m3 correction pass (default 6)
-    if isinstance(precision, tuple):
+    if isinstance(precision, tuple) and precision[1] == "flat":     # without the even / odd plane layout
+        precision = precision[0]
+        monkeypatch.setenv("RISER_EO", "0")
+    elif isinstance(precision, tuple):
         precision, f8_from = precision
         monkeypatch.setenv("RISER_F8_FROM", str(f8_from))
     rng = np.random.default_rng(0)
