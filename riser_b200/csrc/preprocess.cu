@@ -375,44 +375,39 @@ constexpr int kRes = 500;               // _TRIM_RESOLUTION, riser/preprocess.py
 constexpr int kPerLane = (kRes + 31) / 32;   // 16
 constexpr int kMaxWindows = 2048;
 
-// rank-k (0-based) key among this warp's valid keys, bit-serial radix descent with
-// warp-wide counts (REDUX); keys < 2^nbits.
-__device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[kPerLane], const bool (&valid)[kPerLane],
-                                                int nbits, uint32_t k) {
+// rank-k (0-based) key among this warp's keys (all < 2^nbits; padding lanes hold 0xffffffff): binary search
+// on the value, one warp-wide count #{key < T} per bit (REDUX) -- the "warp-shuffle selection" of the north
+// star.  nbits comes from the window's own range, so a 500-sample window costs ~10 steps, not 16.
+__device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[kPerLane], int nbits, uint32_t k) {
   uint32_t prefix = 0;
   for (int bit = nbits - 1; bit >= 0; --bit) {
-    const uint32_t hi_mask = ~((2u << bit) - 1u);
+    const uint32_t t = prefix | (1u << bit);
     int cnt = 0;
 #pragma unroll
-    for (int j = 0; j < kPerLane; ++j)
-      cnt += (valid[j] && ((key[j] & hi_mask) == prefix) && !((key[j] >> bit) & 1u)) ? 1 : 0;
+    for (int j = 0; j < kPerLane; ++j) cnt += (key[j] < t) ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (k >= static_cast<uint32_t>(cnt)) {
-      k -= cnt;
-      prefix |= 1u << bit;
-    }
+    if (k >= static_cast<uint32_t>(cnt)) prefix = t;      // rank k lies at or above t
   }
   return prefix;
 }
 
 // the two middle order statistics (ranks 249 and 250 of 500) -> their sum
-__device__ __forceinline__ uint32_t warp_mid_sum(const uint32_t (&key)[kPerLane], const bool (&valid)[kPerLane],
-                                                 int nbits) {
-  const uint32_t v1 = warp_select(key, valid, nbits, kRes / 2 - 1);
+__device__ __forceinline__ uint32_t warp_mid_sum(const uint32_t (&key)[kPerLane], int nbits) {
+  const uint32_t v1 = warp_select(key, nbits, kRes / 2 - 1);
   int le = 0;
   uint32_t next = 0xffffffffu;
 #pragma unroll
   for (int j = 0; j < kPerLane; ++j) {
-    if (valid[j]) {
-      le += key[j] <= v1 ? 1 : 0;
-      if (key[j] > v1) next = min(next, key[j]);
-    }
+    le += key[j] <= v1 ? 1 : 0;
+    if (key[j] > v1) next = min(next, key[j]);      // (padding keys are 0xffffffff: never the minimum of 500 real keys)
   }
   le = __reduce_add_sync(0xffffffffu, le);
   next = __reduce_min_sync(0xffffffffu, next);
   const uint32_t v2 = (le > kRes / 2) ? v1 : next;
   return v1 + v2;
 }
+
+__device__ __forceinline__ int bits_of(uint32_t v) { return 32 - __clz(v); }
 
 __global__ void __launch_bounds__(kThreads)
 polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
@@ -427,23 +422,48 @@ polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
     const int nw = min(n / kRes, kMaxWindows);
     for (int w = warp; w < nw; w += kWarps) {
       const int16_t* wp = g + w * kRes;
-      uint32_t key[kPerLane];
-      bool valid[kPerLane];
-      int sum = 0;
+      int v[kPerLane];
+      int sum = 0, vmin = 32767, vmax = -32768;
+      bool ok[kPerLane];
+      if ((reinterpret_cast<uintptr_t>(wp) & 3) == 0) {      // 4-byte loads: lane takes sample pairs (which lane holds
+        const uint32_t* wp2 = reinterpret_cast<const uint32_t*>(wp);   // which sample is irrelevant to the statistics)
+#pragma unroll
+        for (int j = 0; j < kPerLane / 2; ++j) {
+          const int idx = j * 32 + lane;
+          ok[2 * j] = ok[2 * j + 1] = idx < kRes / 2;
+          const uint32_t pr = ok[2 * j] ? __ldg(wp2 + idx) : 0u;
+          v[2 * j] = static_cast<int16_t>(pr & 0xffffu);
+          v[2 * j + 1] = static_cast<int16_t>(pr >> 16);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+          const int idx = j * 32 + lane;
+          ok[j] = idx < kRes;
+          v[j] = ok[j] ? static_cast<int>(wp[idx]) : 0;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < kPerLane; ++j) {
-        const int idx = j * 32 + lane;
-        valid[j] = idx < kRes;
-        const int v = valid[j] ? static_cast<int>(wp[idx]) : 0;
-        sum += v;
-        key[j] = static_cast<uint32_t>(v + 32768);
+        sum += v[j];
+        vmin = min(vmin, ok[j] ? v[j] : 32767);
+        vmax = max(vmax, ok[j] ? v[j] : -32768);
       }
       sum = __reduce_add_sync(0xffffffffu, sum);
-      const int med2 = static_cast<int>(warp_mid_sum(key, valid, 16)) - 65536;   // 2 * median
+      vmin = __reduce_min_sync(0xffffffffu, vmin);
+      vmax = __reduce_max_sync(0xffffffffu, vmax);
+      // median on keys x - min (as many bits as the window's range needs)
+      uint32_t key[kPerLane];
 #pragma unroll
       for (int j = 0; j < kPerLane; ++j)
-        key[j] = static_cast<uint32_t>(abs(2 * (static_cast<int>(key[j]) - 32768) - med2));
-      const uint32_t mad4 = warp_mid_sum(key, valid, 18);                         // 4 * MAD
+        key[j] = ok[j] ? static_cast<uint32_t>(v[j] - vmin) : 0xffffffffu;
+      const int med2 = 2 * vmin + static_cast<int>(warp_mid_sum(key, bits_of(static_cast<uint32_t>(vmax - vmin))));   // 2 * median
+      // MAD on keys |2x - 2 median|
+      const uint32_t dmax = static_cast<uint32_t>(max(abs(2 * vmin - med2), abs(2 * vmax - med2)));
+#pragma unroll
+      for (int j = 0; j < kPerLane; ++j)
+        key[j] = ok[j] ? static_cast<uint32_t>(abs(2 * v[j] - med2)) : 0xffffffffu;
+      const uint32_t mad4 = warp_mid_sum(key, bits_of(dmax));                         // 4 * MAD
       if (lane == 0) {
         w_sum[w] = sum;
         w_mad4[w] = static_cast<int32_t>(mad4);
