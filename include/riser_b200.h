@@ -158,15 +158,17 @@ int riser_plan_destroy(riser_plan* p);
  * result equal to classifying it alone.  probs [B, 2] = softmax(logits) =
  * (p_off_target, p_on_target).  A read with len[b] < 4096 gets NaN (the
  * reference raises in max_pool1d for such input).
+ * x must be 16-byte aligned with ld_x a multiple of 4 (>= max_len): the fused layers
+ * 0 + 1 stage the signal with bulk copies (RISER_EINVAL otherwise).  Values beyond
+ * len[b] in a row are never read as signal.
  * feat (optional, may be NULL): fp32 [B, channels[n-1]] pooled features.       */
 int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32_t* len,
                   float* probs, float* feat, riser_stream_t stream);
 
 /* The stages of riser_forward, callable separately so that a caller can put CUDA
  * events between them (bench.py times the conv stack):
- *   0 = layer 0 (CUDA cores) + the memory-bound early conv layers, run chunk of reads by
- *       chunk of reads so their activations stay in the L2;
- *   1 = the remaining conv layers over the whole batch (tcgen05);  2 = head;
+ *   0 = tile activity flags (+ layer 0 when it is not fused into layer 1's launch);
+ *   1 = the conv layers (tcgen05; layers 0 + 1 are one launch by default);  2 = head;
  *   3 = the layer-0 launches of stage 0 alone (timing aid, not part of riser_forward). */
 int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
                         const int32_t* len, float* probs, float* feat, riser_stream_t stream);
