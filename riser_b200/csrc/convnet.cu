@@ -139,6 +139,7 @@ struct ActivityArgs {
 struct LayerPlan {
   CUtensorMap tm_a, tm_b, tm_a8, tm_b8;   // (EO layers: tm_a = E plane, tm_a8 = O plane)
   int eo = 0;                             // input in the even / odd plane layout -> conv_eo_kernel
+  int pair = 0;                           // CTA pairs (cta_group::2) -> conv_pair_kernel
   ConvArgs args;
   int n_supers_total = 0;
   int rows_per_super = 0;   // flat input rows one work item covers (ms * 128; 510 for the fused layers 0+1)
@@ -1662,6 +1663,251 @@ EoKernelFn pick_conv_eo(int ms, int planes, int wplanes) {
 }
 
 // ------------------------------------------------------------------------------------
+// Wide layers on CTA pairs (cta_group::2, clusters of two CTAs; F16_F8 layers with streamed weights).
+//
+// One M = 256 MMA spans both SMs of a pair: each CTA stages 128 rows of A (its half of a 256-row
+// sub-tile) and HALF of the N rows of every weight tile, so the weight bytes streamed from L2 and the
+// shared-memory operand bytes read per MAC are halved per SM -- which is what bounds the e4m3 pass
+// of these layers (a one-CTA e4m3 MMA at N = 192 needs 213 B/clk of operands).  The leader CTA's
+// thread issues the MMAs; TMA loads of both CTAs complete on the leader's "full" barriers
+// (cp.async.bulk.tensor ... cta_group::2 with the peer bit cleared), tcgen05.commit multicasts the
+// "empty" / "accumulator full" arrivals to both CTAs, and the peer's epilogue warps release the
+// accumulators on the leader's barrier (mapa + remote arrive).
+// Work item of a pair = (MS sub-tiles of 256 flat rows, N tile); both CTAs walk the same item list.
+template <int MS>
+__global__ void __launch_bounds__(64 + 128 * kMaxEpiSets, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_b8,
+                 const ConvArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  constexpr uint32_t kATile = 136 * 128;
+  constexpr uint32_t kAGroup = MS * kATile;
+  const uint32_t b_bytes = (a.n_tile / 2) * 128;           // this CTA's half of a weight tile
+  unsigned char* a_ring = base;
+  unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroup;
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + static_cast<size_t>(a.b_stages) * b_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
+  const int n_items = a.n_supers * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_a8);
+    tma_prefetch_desc(&tm_b8);
+    for (int i = 0; i < a.a_stages; ++i) {
+      mbar_init(&s.a_full[i], 1);
+      mbar_init(&s.a_empty[i], 1);
+    }
+    for (int i = 0; i < a.b_stages; ++i) {
+      mbar_init(&s.b_full[i], 1);
+      mbar_init(&s.b_empty[i], 1);
+    }
+    for (int i = 0; i < a.acc_stages; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      for (int ms = 0; ms < MS; ++ms) mbar_init(&s.tmem_empty[i][ms], 2 * 4 * a.epi_sets);   // both CTAs' warps
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&s.tmem_base, kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  // item -> (M super-tile, N tile), N fastest; the pair visits item = pair, pair + n_pairs_grid, ...
+  auto item_super = [&](int item) { return a.super0 + item / a.n_tiles; };
+  auto item_n = [&](int item) { return item % a.n_tiles; };
+  auto active = [&](int item) { return !a.flags || __ldg(a.flags + item_super(item)) != 0; };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int item = pair; item < n_items; item += n_pairs_grid) {
+        if (!active(item)) continue;
+        const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM - 1;
+        const int n0 = item_n(item) * a.n_tile + static_cast<int>(rank) * (a.n_tile / 2);
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          const bool is8 = kb >= a.kb16;
+          mbar_wait(&s.a_empty[sa], pa ^ 1);
+          if (leader) mbar_arrive_expect_tx(&s.a_full[sa], 2 * MS * kATile);
+          unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroup;
+#pragma unroll
+          for (int ms = 0; ms < MS; ++ms) {
+            if (is8)
+              tma_load_2d_pair(dst + ms * kATile, &tm_a8, &s.a_full[sa], 2 * a.cin_p + (kb - a.kb16) * 128, m0 + ms * 256);
+            else
+              tma_load_2d_pair(dst + ms * kATile, &tm_a, &s.a_full[sa], kb * 64, m0 + ms * 256);
+          }
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(&s.b_empty[sb], pb ^ 1);
+            if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_bytes);
+            if (is8)
+              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b8, &s.b_full[sb], (kb - a.kb16) * 128,
+                               tap * a.cout_p + n0);
+            else
+              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * 64,
+                               tap * a.cout_p + n0);
+            if (++sb == a.b_stages) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      int sa = 0, sb = 0, stage = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
+      const int nk_last = (a.cin_p - (a.kb16 - 1) * 64) / 16;
+      const int nk_last8 = (2 * a.cin_p - (a.k_blocks - a.kb16 - 1) * 128) / 32;
+      const uint32_t acc_stride = MS * a.acc_cols;
+      for (int item = pair; item < n_items; item += n_pairs_grid) {
+        if (!active(item)) continue;
+        const uint32_t d_base = tmem_base + stage * acc_stride;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          const bool is8 = kb >= a.kb16;
+          const int nk = is8 ? ((kb == a.k_blocks - 1) ? nk_last8 : 4) : ((kb == a.kb16 - 1) ? nk_last : 4);
+          mbar_wait(&s.a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_addr = a_ring_addr + sa * kAGroup;
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            mbar_wait(&s.b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t db = sw_desc<false>(b_region_addr + sb * b_bytes);
+#pragma unroll
+            for (int ms = 0; ms < MS; ++ms) {
+              if (kb == 0 && tap == 0) {       // first touch of this accumulator: both CTAs have drained it
+                mbar_wait(&s.tmem_empty[stage][ms], acc_phase ^ 1);
+                tc_fence_after();
+              }
+              const uint64_t da = sw_desc<false>(a_addr + ms * kATile + tap * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < nk) {
+                  if (is8) umma_f8_pair(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
+                  else umma_f16_pair(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, (kb | tap | k) != 0);
+                }
+            }
+            umma_commit_pair(&s.b_empty[sb]);
+            if (++sb == a.b_stages) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          umma_commit_pair(&s.a_empty[sa]);
+          if (++sa == a.a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit_pair(&s.tmem_full[stage]);
+        if (++stage == a.acc_stages) {
+          stage = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 2 + 4 * a.epi_sets) {
+    // ===================== epilogue (both CTAs, each its own 128 accumulator rows) =====================
+    const int q = warp & 3;
+    const int eset = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    const int epi_threads = 128 * a.epi_sets;
+    const bool odd = lane & 1;
+    const int row_elems = a.cout_p * a.out_planes;
+    const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
+    const int n_chunks = a.n_tile >> 4;
+    int stage = 0, it = -1;
+    uint32_t acc_phase = 0;
+    for (int item = pair; item < n_items; item += n_pairs_grid) {
+      if (!active(item)) continue;
+      ++it;
+      const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM;
+      const int n0 = item_n(item) * a.n_tile;
+      float* bias_s = s.bias[it & 1];
+      for (int i = et; i < a.n_tile; i += epi_threads) bias_s[i] = a.bias[n0 + i];
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+      bool valid[MS], writable[MS];
+      int64_t out_row[MS];
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        valid[ms] = writable[ms] = false;
+        out_row[ms] = 0;
+        const int r_even = (m0 + ms * 256 + 32 * q + lane) & ~1;
+        if (r_even < a.rows_in) {
+          const uint32_t pidx = static_cast<uint32_t>(r_even) >> 1;
+          const int b = static_cast<int>((static_cast<unsigned long long>(pidx) * a.pair_magic) >> 40);
+          const int tp = static_cast<int>(pidx) - b * a.half_lp;
+          valid[ms] = tp < (__ldg(a.len0 + b) >> a.shift);
+          writable[ms] = tp < a.Lp_out;
+          out_row[ms] = static_cast<int64_t>(b) * a.Lp_out + tp;
+        }
+      }
+      mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
+      tc_fence_after();
+      int u = eset;
+#pragma unroll
+      for (int ms = 0; ms < MS; ++ms) {
+        void* orow = a.out_fp32
+                         ? static_cast<void*>(static_cast<float*>(a.out) + out_row[ms] * row_elems + n0)
+                         : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + (stage * MS + ms) * a.acc_cols;
+        for (; u < (ms + 1) * n_chunks; u += a.epi_sets) {
+          const int c = u - ms * n_chunks;
+          uint32_t v[16];
+          tmem_ld_32x16(t_addr + c * 16, v);
+          tmem_ld_wait();
+          uint8_t* f8_row = nullptr;
+          if (a.out_f8)
+            f8_row = static_cast<uint8_t*>(a.out) + out_row[ms] * row_elems * 2 + 2 * a.cout_p + n0;
+          epilogue_chunk16(v, bias_s, c * 16, odd, valid[ms], writable[ms], orow, a.out_fp32, lo_off,
+                           a.w_inv_scale, f8_row, a.cout_p);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&s.tmem_empty[stage][ms], 0);   // on the leader's barrier
+      }
+      if (++stage == a.acc_stages) {
+        stage = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still be read by the leader's MMAs / signalled until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+PairKernelFn pick_conv_pair(int ms) { return ms == 2 ? conv_pair_kernel<2> : conv_pair_kernel<1>; }
+
+// ------------------------------------------------------------------------------------
 // Per-layer activity flags of the M super-tiles: a super-tile is active when at least one of
 // its row pairs has pooled index t' <= valid output length of its read (the "<=" keeps the
 // zero row that terminates every read written).  Ragged batches and skipped reads (len 0)
@@ -2180,6 +2426,25 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fixed + w_eo + static_cast<size_t>(a.a_stages) * a.ms * group1;
       lp.rows_per_super = a.ms * 2 * kBlockM;
     }
+    if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 0)) {
+      // conv_pair_kernel: M = 256 over two CTAs, each holds 128 rows of A and half of every weight tile
+      lp.pair = 1;
+      int st2 = make_tmap(&lp.tm_b, L.w, L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
+      if (!st2) st2 = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
+      if (st2) {
+        delete p;
+        return st2;
+      }
+      a.idesc = umma_idesc_f16(256, L.n_tile);
+      a.ms = (2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 2) >= 2) ? 2 : 1;
+      const size_t a_group = static_cast<size_t>(a.ms) * 136 * 128, half_b = static_cast<size_t>(L.n_tile / 2) * 128;
+      a.a_stages = env_int("RISER_PAIR_ASTAGES", 3);
+      a.b_stages = std::max(2, std::min<int>(kMaxBStages, static_cast<int>((avail - a.a_stages * a_group) / half_b)));
+      a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+      a.epi_sets = 4;
+      lp.smem = fixed + a.a_stages * a_group + a.b_stages * half_b;
+      lp.rows_per_super = a.ms * 256;
+    }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
   }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
@@ -2212,6 +2477,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     for (int pl = 0; pl < 3; ++pl)
       RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_eo(ms, pl == 2 ? 2 : 1, pl == 0 ? 1 : 2)),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  for (int ms = 1; ms <= 2; ++ms)
+    RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_pair(ms)),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   for (int pl = 0; pl < 4; ++pl)
     RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl)),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -2301,6 +2569,23 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
     pick_fused01(a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(
         lp.tm_b, lp.tm_b8, a);
     RISER_CUDA_TRY(cudaGetLastError());
+    return RISER_OK;
+  }
+  if (lp.pair) {
+    cudaLaunchConfig_t cfg = {};
+    const int n_items = a.n_supers * a.n_tiles;
+    cfg.gridDim = dim3(static_cast<unsigned>(std::min(2 * n_items, p->model->sm_count & ~1)));
+    cfg.blockDim = dim3(64 + 128 * a.epi_sets);
+    cfg.dynamicSmemBytes = lp.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RISER_CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_conv_pair(a.ms), lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, a));
     return RISER_OK;
   }
   if (lp.eo) {

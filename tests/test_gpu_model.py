@@ -52,13 +52,17 @@ def oracle_layers(state, x):
                                             (1, PREC_F16_W2), (1, PREC_F16_X3), (2, PREC_F16), (2, PREC_F16_W2),
                                             (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8),
                                             (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3)),
-                                            (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat"))])
+                                            (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat")),
+                                            (2, (PREC_F16_F8, "pair"))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
     f8_from = 6                      # F16_F8: first layer that runs the e4m3 correction pass (default 6)
     if isinstance(precision, tuple) and precision[1] == "flat":     # without the even / odd plane layout
         precision = precision[0]
         monkeypatch.setenv("RISER_EO", "0")
+    elif isinstance(precision, tuple) and precision[1] == "pair":   # layers 6-11 on CTA pairs (cta_group::2), opt-in
+        precision = precision[0]
+        monkeypatch.setenv("RISER_PAIR", "1")
     elif isinstance(precision, tuple):
         precision, f8_from = precision
         monkeypatch.setenv("RISER_F8_FROM", str(f8_from))
