@@ -15,7 +15,7 @@ sys.path.insert(0, ".")
 from riser_b200 import Kit, SignalProcessor, Model, BatchedClassifier, RaggedBatch, synth   # noqa: E402
 from riser_b200.config import shipped_config                                                # noqa: E402
 
-prec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+prec = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 log = logging.getLogger("sweep")
 dev = torch.device("cuda")
 
