@@ -210,3 +210,57 @@ def test_plan_reuse_with_stale_activations_and_skipped_reads(precision):
     # and again with the long reads: buffers now hold the short batch's leftovers
     p3 = model.classify_batch(x, lens, max_len=12048).cpu().numpy()
     assert np.array_equal(p3, p1)
+
+
+@pytest.mark.parametrize("max_len", [16000, 12048, 8615, 4099, 4096, 9999])
+def test_random_ragged_batches_all_boundaries(max_len):
+    """Random ragged lengths (and a few zeros) for several max_len values, default precision: work items of the
+    fused layers 0+1 (255 pooled outputs) and of the even/odd layers straddle read boundaries at arbitrary offsets,
+    Lp parities differ, and the shortest reads end long before the tiles do."""
+    rng = np.random.default_rng(1000 + max_len)
+    state = synth.state_dict(2)
+    model = Model(state, CFG, LOG, "globin")
+    B = 23
+    lengths = [int(x) for x in rng.integers(4096, max_len + 1, size=B)]
+    lengths[0], lengths[1], lengths[-1] = max_len, 4096, max_len
+    lengths[5] = 0
+    if max_len > 4097:
+        lengths[7] = 4097
+    normed = [pp.mad_normalise(synth.body(rng, n)) if n else np.zeros(0) for n in lengths]
+    ld = (max_len + 3) & ~3
+    x = torch.full((B, ld), 3.25)                      # poison beyond each read's length
+    for b, v in enumerate(normed):
+        x[b, :len(v)] = torch.from_numpy(np.asarray(v, dtype=np.float64)).float()
+    lens = torch.tensor(lengths, dtype=torch.int32).cuda()
+    probs = model.classify_batch(x.cuda(), lens, max_len=max_len).cpu().numpy()
+    live = [b for b, n in enumerate(lengths) if n]
+    want = net.classify_ragged(state, [normed[b] for b in live])
+    assert np.abs(probs[live] - want).max() < 1e-3, np.abs(probs[live] - want).max()
+    assert np.isnan(probs[5]).all()
+
+
+def test_full_size_batch_replication_invariance():
+    """BASELINE config 2 at full size (4096 x 16,000): the batch is 37 distinct reads (ragged, one skipped)
+    repeated to 4096 rows.  Every replica must give bit-identical probabilities whatever its row (tiles of
+    different CTAs, different positions inside work items), and the first copies must match the oracle."""
+    rng = np.random.default_rng(77)
+    state = synth.state_dict(0)
+    model = Model(state, CFG, LOG, "mRNA")
+    B, L, K = 4096, 16000, 37
+    lengths = [int(v) for v in rng.integers(4096, L + 1, size=K)]
+    lengths[0], lengths[3], lengths[9] = L, 4096, 0
+    normed = [pp.mad_normalise(synth.body(rng, n)) if n else np.zeros(0) for n in lengths]
+    xk = torch.zeros(K, L)
+    for b, v in enumerate(normed):
+        xk[b, :len(v)] = torch.from_numpy(np.asarray(v, dtype=np.float64)).float()
+    idx = torch.arange(B) % K
+    x = xk[idx].cuda()
+    lens = torch.tensor(lengths, dtype=torch.int32)[idx].cuda()
+    probs = model.classify_batch(x, lens, max_len=L).cpu().numpy()
+    first = probs[:K]
+    live = [b for b in range(K) if lengths[b]]
+    want = net.classify_ragged(state, [normed[b] for b in live])
+    assert np.abs(first[live] - want).max() < 1e-3
+    rep = probs.reshape(-1)[: (B // K) * K * 2].reshape(B // K, K, 2)
+    assert np.array_equal(rep[:, live], np.broadcast_to(first[live], rep[:, live].shape))
+    assert np.isnan(rep[:, 9]).all()
