@@ -112,6 +112,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// L2 prefetch of a 16-byte aligned global range (multiple of 16 bytes): no destination, no completion.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes)
+               : "memory");
+}
+
 // 1-D bulk copy global -> shared (16-byte aligned source, destination and size), completion
 // on an mbarrier (complete_tx::bytes).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

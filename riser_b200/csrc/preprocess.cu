@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace riser {
 namespace {
@@ -21,17 +22,21 @@ constexpr int kBins = 2048;             // first-pass histogram bins
 constexpr int kBinsPerThread = kBins / kThreads;
 constexpr int kSubBins = 128;           // refinement pass (shift <= 7)
 constexpr int kMaxLen = 98304;          // samples staged in smem (192 KB)
+constexpr int kMaxRuns = 1024;          // outlier-run start indices collected per read (more: rescan path)
 
 constexpr double kOutlierLimit = 3.5;   // riser/preprocess.py:6
 constexpr double kScalingFactor = 1.4826;  // riser/preprocess.py:7
 
 struct SelectScratch {
+  uint64_t bar[2];      // one mbarrier per staging buffer (bulk-copy completion)
   uint32_t hist[kBins];
   uint32_t sub[kSubBins];
   uint32_t warp_sums[kWarps];
   uint32_t res[4];      // bin1, before1, bin2, before2
   uint32_t refined;
+  uint32_t n_runs;
   int32_t red[2 * kWarps];
+  int32_t runs[kMaxRuns];
 };
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums) {
@@ -50,19 +55,59 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   return base + inc - v;
 }
 
-// Exact order statistics k1 <= k2 (0-based) of the n keys key(0..n-1), all <= maxkey.
+// A window of n samples staged in shared memory at the 16-byte phase it has in global memory:
+// sample i is stage[a + i], 0 <= a < 8.  for_each() hands every sample of the window to f, one
+// 16-byte chunk (8 samples) per thread and step; the two edge chunks are masked.
+struct StagedWindow {
+  const int16_t* stage;
+  int a, n;
+  __device__ __forceinline__ int operator[](int i) const { return stage[a + i]; }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const {
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+    const int end = a + n;
+    const int n_chunks = (end + 7) >> 3;
+    for (int c = threadIdx.x; c < n_chunks; c += kThreads) {
+      const uint4 v = s4[c];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const int base = 8 * c;
+      if (base >= a && base + 8 <= end) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f(static_cast<int>(static_cast<int16_t>(w[j] & 0xffffu)));
+          f(static_cast<int>(static_cast<int16_t>(w[j] >> 16)));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int p = base + j;
+          if (p >= a && p < end) f(static_cast<int>(static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu)));
+        }
+      }
+    }
+  }
+};
+
+// Exact order statistics k1 <= k2 (0-based) of the keys key(sample) over the window, all <= maxkey.
 // Pass A: histogram of key >> shift with shift chosen so that it fits kBins; block scan
 // locates the bins holding the two ranks.  Pass B (only when shift > 0): histogram of the
 // low bits inside the located bin.  Block-uniform control flow; all threads get r1, r2.
 template <class KeyFn>
-__device__ int select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32_t k2,
-                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false) {
+__device__ int select_two(KeyFn key, const StagedWindow& win, uint32_t maxkey, uint32_t k1, uint32_t k2,
+                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false, int dbg = 0) {
   const int tid = threadIdx.x;
   int shift = 0;
   while ((maxkey >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
   for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += kThreads) atomicAdd(&s.hist[key(i) >> shift], 1u);
+  if (dbg & 2) {          // timing experiment: loads and keys, no atomics
+    uint32_t acc = 0;
+    win.for_each([&](int e) { acc += key(e) >> shift; });
+    if (acc == 0x12345678u) s.hist[0] = acc;
+    if (tid == 0) s.hist[maxkey >> (shift + 1)] = win.n;
+  } else {
+    win.for_each([&](int e) { atomicAdd(&s.hist[key(e) >> shift], 1u); });
+  }
   __syncthreads();
   uint32_t c[kBinsPerThread];
   uint32_t local = 0;
@@ -111,10 +156,10 @@ __device__ int select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32
     __syncthreads();
     for (int i = tid; i < kSubBins; i += kThreads) s.sub[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += kThreads) {
-      const uint32_t kx = key(i);
+    win.for_each([&](int e) {
+      const uint32_t kx = key(e);
       if ((kx >> shift) == bin) atomicAdd(&s.sub[kx & mask], 1u);
-    }
+    });
     __syncthreads();
     if (tid == 0) {
       uint32_t run = 0, found = 0;
@@ -131,10 +176,6 @@ __device__ int select_two(KeyFn key, int n, uint32_t maxkey, uint32_t k1, uint32
   return shift;
 }
 
-__device__ __forceinline__ double norm_value(int x, double median, double denom) {
-  // (x - median) / (1.4826 * mad), riser/preprocess.py:122-125, IEEE round-to-nearest
-  return __ddiv_rn(__dsub_rn(static_cast<double>(x), median), denom);
-}
 __device__ __forceinline__ double clip_outlier(double v) {
   // riser/preprocess.py:141-147
   if (v > kOutlierLimit) return kOutlierLimit;
@@ -142,66 +183,106 @@ __device__ __forceinline__ double clip_outlier(double v) {
   return v;
 }
 
+// Kernel structure (one CTA per read, persistent over reads b = blockIdx.x, + gridDim.x, ...):
+//   stage    one 1-D bulk copy (cp.async.bulk, mbarrier complete_tx) of the 16-byte blocks that hold the
+//            window; with two staging buffers the copy of the CTA's NEXT read is issued before the
+//            current one is processed, so the global-load latency is off the critical path
+//   min/max  packed 16-bit min / max over the staged chunks
+//   median   histogram radix select (select_two); MAD from the same histogram by a warp-wide
+//            32-ary search on the distance (or a second select when the range needed a shift)
+//   normalise + smooth: every sample gets the exact quotient; the starts of outlier runs are collected
+//            in shared memory and walked afterwards, one run per thread, so a rare outlier no longer
+//            stalls its whole warp in a divergent slow path
 __global__ void __launch_bounds__(kThreads)
 normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
                  const int32_t* __restrict__ start, const int32_t* __restrict__ len, int B,
-                 float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ med2_mad4) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                 float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ med2_mad4,
+                 int nbuf, int buf_samples, int dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   SelectScratch& s = *reinterpret_cast<SelectScratch*>(smem_raw);
-  int16_t* stage = reinterpret_cast<int16_t*>(smem_raw + ((sizeof(SelectScratch) + 15) & ~size_t(15)));
+  int16_t* stage_base = reinterpret_cast<int16_t*>(smem_raw + ((sizeof(SelectScratch) + 127) & ~size_t(127)));
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  if (tid == 0) {
+    mbar_init(&s.bar[0], 1);
+    mbar_init(&s.bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // thread 0: bulk copy of read r's window (whole 16-byte blocks) into staging buffer `buf`
+  auto issue = [&](int r, int buf) {
+    const int nr = len[r];
+    if (nr <= 0) return;
+    const int16_t* gr = sig + off[r] + (start ? start[r] : 0);
+    const int ar = static_cast<int>((reinterpret_cast<uintptr_t>(gr) >> 1) & 7);
+    const uint32_t bytes = static_cast<uint32_t>(((ar + nr + 7) >> 3) << 4);
+    mbar_arrive_expect_tx(&s.bar[buf], bytes);
+    bulk_load_1d(stage_base + static_cast<size_t>(buf) * buf_samples, gr - ar, bytes, &s.bar[buf]);
+  };
+  // one staging buffer: the NEXT read's blocks are pulled into L2 while this one is processed, so that its
+  // copy at the top of the next iteration is an L2 hit and the HBM reads spread over the compute phases
+  auto prefetch = [&](int r) {
+    const int nr = len[r];
+    if (nr <= 0) return;
+    const int16_t* gr = sig + off[r] + (start ? start[r] : 0);
+    const int ar = static_cast<int>((reinterpret_cast<uintptr_t>(gr) >> 1) & 7);
+    bulk_prefetch_l2(gr - ar, static_cast<uint32_t>(((ar + nr + 7) >> 3) << 4));
+  };
+  if (nbuf == 2 && tid == 0) issue(blockIdx.x, 0);
+  uint32_t phase_bits = 0;             // bit `buf` = parity the next wait on bar[buf] uses
+
+  int it = 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+    const int buf = (nbuf == 2) ? (it & 1) : 0;
+    if (tid == 0) {
+      if (nbuf == 2) {
+        if (b + static_cast<int>(gridDim.x) < B) issue(b + gridDim.x, buf ^ 1);
+      } else {
+        issue(b, 0);
+        if (b + static_cast<int>(gridDim.x) < B) prefetch(b + gridDim.x);
+      }
+    }
     const int n = len[b];
-    if (n <= 0) continue;
+    if (n <= 0) continue;                 // block-uniform; nothing was issued for this read
     const int16_t* g = sig + off[b] + (start ? start[b] : 0);
     float* o = out + static_cast<int64_t>(b) * ld_out;
-
-    // ---- stage the window in smem at the same 16-byte phase as in global memory
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 1) & 7);
-    const int16_t* x = stage + a;                    // x[i] == g[i]
-    const int n_chunks = (a + n + 7) >> 3;
-    const uint4* g4 = reinterpret_cast<const uint4*>(g - a);
-    uint4* s4 = reinterpret_cast<uint4*>(stage);
+    const int16_t* stage = stage_base + static_cast<size_t>(buf) * buf_samples;
+    const StagedWindow x{stage, a, n};     // x[i] == g[i]
+    mbar_wait(&s.bar[buf], (phase_bits >> buf) & 1u);
+    phase_bits ^= 1u << buf;
+
+    // ---- min / max of the window (packed 16-bit lanes for whole chunks)
     int vmin = 32767, vmax = -32768;
-    auto take16 = [&](const uint4& v) {
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    {
+      uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
+      const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+      const int end = a + n;
+      const int n_chunks = (end + 7) >> 3;
+      for (int c = tid; c < n_chunks; c += kThreads) {
+        const uint4 v = s4[c];
+        const int base = 8 * c;
+        if (base >= a && base + 8 <= end) {
+          mn2 = __vimin3_s16x2(mn2, v.x, v.y);
+          mn2 = __vimin3_s16x2(mn2, v.z, v.w);
+          mx2 = __vimax3_s16x2(mx2, v.x, v.y);
+          mx2 = __vimax3_s16x2(mx2, v.z, v.w);
+        } else {
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e0 = static_cast<int16_t>(w[j] & 0xffff);
-        const int e1 = static_cast<int16_t>(w[j] >> 16);
-        vmin = min(vmin, min(e0, e1));
-        vmax = max(vmax, max(e0, e1));
-      }
-    };
-    // interior chunks (fully inside the window) are 16-byte loads, four in flight per thread;
-    // the (at most two) edge chunks are peeled into scalar loads
-    const int c_lo = (a > 0) ? 1 : 0;
-    const int c_hi = (a + n) >> 3;          // chunks [c_lo, c_hi) are interior
-    for (int c = c_lo + tid; c < c_hi; c += 4 * kThreads) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c + u * kThreads < c_hi) v[u] = __ldg(g4 + c + u * kThreads);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (c + u * kThreads < c_hi) {
-          s4[c + u * kThreads] = v[u];
-          take16(v[u]);
-        }
-    }
-    if (tid < 2) {
-      const int c = tid ? c_hi : 0;
-      if ((tid == 0 && c_lo == 1) || (tid == 1 && c_hi < n_chunks && !(c_hi == 0 && c_lo == 1))) {
-        const int lo = 8 * c - a;
-        for (int i = max(lo, 0); i < min(lo + 8, n); ++i) {
-          const int e = g[i];
-          stage[a + i] = static_cast<int16_t>(e);
-          vmin = min(vmin, e);
-          vmax = max(vmax, e);
+          for (int j = 0; j < 8; ++j) {
+            const int p = base + j;
+            if (p >= a && p < end) {
+              const int e = static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+              vmin = min(vmin, e);
+              vmax = max(vmax, e);
+            }
+          }
         }
       }
+      vmin = min(vmin, min(static_cast<int>(static_cast<int16_t>(mn2 & 0xffffu)), static_cast<int>(static_cast<int16_t>(mn2 >> 16))));
+      vmax = max(vmax, max(static_cast<int>(static_cast<int16_t>(mx2 & 0xffffu)), static_cast<int>(static_cast<int16_t>(mx2 >> 16))));
     }
     vmin = __reduce_min_sync(0xffffffffu, vmin);
     vmax = __reduce_max_sync(0xffffffffu, vmax);
@@ -222,8 +303,8 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     const uint32_t k1 = static_cast<uint32_t>((n - 1) >> 1), k2 = static_cast<uint32_t>(n >> 1);
     uint32_t r1, r2;
     const int range = vmax - vmin;
-    const int shift_used = select_two([&](int i) { return static_cast<uint32_t>(x[i] - vmin); }, n,
-                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true);
+    const int shift_used = select_two([&](int e) { return static_cast<uint32_t>(e - vmin); }, x,
+                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true, dbg);
     const int med2 = 2 * vmin + static_cast<int>(r1 + r2);
 
     // ---- MAD on keys d = |2x - med2| = 2|x - median| -> mad4 = 4 * MAD (exact)
@@ -232,26 +313,29 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     if (shift_used == 0) {
       // The value histogram already holds the whole distribution: with P[u] = #{x - vmin <= u}
       // and m = med2 - 2*vmin, #{|2x - med2| <= d} = P[floor((m+d)/2)] - P[ceil((m-d)/2) - 1];
-      // the two middle order statistics of d are found by bisection on d (threads 0 and 1).
-      if (tid < 2) {
+      // the two middle order statistics of d are found by a 32-ary search on d (warps 0 and 1,
+      // one probe per lane and round: 3 rounds for an 11-bit distance).
+      if (warp < 2) {
         const int m = static_cast<int>(r1 + r2);
-        const uint32_t want = (tid ? k2 : k1) + 1;
-        int lo_d = 0, hi_d = static_cast<int>(dmax);
+        const uint32_t want = (warp ? k2 : k1) + 1;
+        int lo_d = 0, hi_d = static_cast<int>(dmax);      // invariant: count(hi_d) >= want
         while (lo_d < hi_d) {
-          const int d = (lo_d + hi_d) >> 1;
-          int hi_u = (m + d) >> 1;
-          hi_u = min(hi_u, range);
-          const int lo_u = (m - d + 1) >> 1;                 // ceil((m - d) / 2), may be <= 0
+          const int step = (hi_d - lo_d + 32) >> 5;       // ceil(span / 32)
+          const int d = min(lo_d + (lane + 1) * step - 1, hi_d);
+          const int hi_u = min((m + d) >> 1, range);
+          const int lo_u = (m - d + 1) >> 1;              // ceil((m - d) / 2), may be <= 0
           const uint32_t cnt = s.hist[hi_u] - (lo_u > 0 ? s.hist[lo_u - 1] : 0u);
-          if (cnt >= want) hi_d = d; else lo_d = d + 1;
+          const uint32_t okm = __ballot_sync(0xffffffffu, cnt >= want);   // lane 31 probes hi_d: never empty
+          const int f = __ffs(okm) - 1;
+          hi_d = min(lo_d + (f + 1) * step - 1, hi_d);
+          lo_d = lo_d + f * step;
         }
-        s.res[tid] = static_cast<uint32_t>(lo_d);
+        if (lane == 0) s.res[warp] = static_cast<uint32_t>(lo_d);
       }
       __syncthreads();
       mad4 = s.res[0] + s.res[1];
-      __syncthreads();
     } else {
-      select_two([&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)); }, n, dmax, k1, k2,
+      select_two([&](int e) { return static_cast<uint32_t>(abs(2 * e - med2)); }, x, dmax, k1, k2,
                  s, r1, r2);
       mad4 = r1 + r2;
     }
@@ -270,98 +354,134 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
           for (int i = i0; i < n; ++i) o[i] = 0.f;
         }
       }
+    } else {
+      const double denom = __dmul_rn(kScalingFactor, static_cast<double>(mad4) * 0.25);
+      // (x - median) / denom == k / D with k = 2x - 2*median (an exact small integer) and D = 2 * denom
+      // (exact).  With y = RN(1/D), q0 = RN(k*y), e = k - q0*D (exact in one FMA), RN(q0 + e*y) is the
+      // correctly rounded quotient (Markstein's final division step), i.e. bit-identical to the reference's
+      // float64 divide at 3 FP64 ops instead of a full DDIV.
+      const double Dd = __dmul_rn(2.0, denom);
+      const double yrcp = __ddiv_rn(1.0, Dd);
+      auto quot = [&](int ki) {
+        const double k = static_cast<double>(ki);
+        const double q0 = __dmul_rn(k, yrcp);
+        const double e = __fma_rn(-q0, Dd, k);
+        return __fma_rn(e, yrcp, q0);
+      };
+      // A window holds at most range + 1 distinct values (~1,000 for a squiggle against 4,096-16,000 samples),
+      // and the float64 pipe is what bounds this kernel: when the value range fits the histogram, the fp32 result
+      // of every VALUE is tabulated once (in the histogram's storage, free after the MAD search) and the per-sample
+      // work becomes one shared-memory look-up.
+      const bool use_lut = (shift_used == 0) && !(dbg & 8);
+      float* lut = reinterpret_cast<float*>(s.hist);
+      if (use_lut)
+        for (int u = tid; u <= range; u += kThreads) lut[u] = static_cast<float>(quot(2 * (vmin + u) - med2));
+
+      // ---- outlier threshold in the integer key domain: |z| > 3.5  <=>  d > dthr, where
+      //      z = fl((d/2) / denom) is monotone in d.  Found once per read with exact divides: the lanes of
+      //      warp 0 test the 32 candidates around 7 * denom at once (serial search as a fallback).
+      if (warp == 0) {
+        auto zval = [&](int d) { return __ddiv_rn(static_cast<double>(d) * 0.5, denom); };
+        const int base = static_cast<int>(__dmul_rn(7.0, denom));
+        const int d = base - 8 + lane;
+        const uint32_t okm = __ballot_sync(0xffffffffu, d < 0 || zval(d) <= kOutlierLimit);
+        if (lane == 0) {
+          const int cnt = __popc(okm);
+          int d0;
+          if (cnt > 0 && cnt < 32 && okm == ((1u << cnt) - 1u)) {
+            d0 = base - 9 + cnt;
+          } else {
+            d0 = base;
+            while (zval(d0 + 1) <= kOutlierLimit) ++d0;
+            while (d0 > 0 && zval(d0) > kOutlierLimit) --d0;
+          }
+          s.refined = static_cast<uint32_t>(max(d0, 0));
+          s.n_runs = 0;
+        }
+      }
       __syncthreads();
-      continue;
-    }
-
-    const double median = static_cast<double>(med2) * 0.5;
-    const double mad = static_cast<double>(mad4) * 0.25;
-    const double denom = __dmul_rn(kScalingFactor, mad);
-
-    // ---- outlier threshold in the integer key domain: |z| > 3.5  <=>  d > dthr, where
-    //      z = fl((d/2) / denom) is monotone in d.  Found once per read with exact divides.
-    if (tid == 0) {
-      auto zval = [&](uint32_t d) { return __ddiv_rn(static_cast<double>(d) * 0.5, denom); };
-      uint32_t d0 = static_cast<uint32_t>(__dmul_rn(7.0, denom));
-      while (zval(d0 + 1) <= kOutlierLimit) ++d0;
-      while (d0 > 0 && zval(d0) > kOutlierLimit) --d0;
-      s.refined = d0;
-    }
-    __syncthreads();
-    const uint32_t dthr = s.refined;
-    auto flagged = [&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)) > dthr; };
-    // Bulk path: (x - median) / denom == k / D with k = 2x - 2*median (an exact small integer)
-    // and D = 2 * denom (exact).  With y = RN(1/D), q0 = RN(k*y), e = k - q0*D (exact in one
-    // FMA), RN(q0 + e*y) is the correctly rounded quotient (Markstein's final division step),
-    // i.e. bit-identical to the reference's float64 divide at 3 FP64 ops instead of a full DDIV.
-    const double Dd = __dmul_rn(2.0, denom);
-    const double yrcp = __ddiv_rn(1.0, Dd);
-    auto fast_k = [&](int ki) {
-      const double k = static_cast<double>(ki);
-      const double q0 = __dmul_rn(k, yrcp);
-      const double e = __fma_rn(-q0, Dd, k);
-      return static_cast<float>(__fma_rn(e, yrcp, q0));
-    };
-    auto fast_norm = [&](int xv) { return fast_k(2 * xv - med2); };
-
-    // ---- normalise + smooth, 4 samples per thread-iteration, 16-byte stores
-    for (int gidx = tid; gidx < n_groups; gidx += kThreads) {
-      const int i0 = 4 * gidx;
-      if (i0 + 4 <= n) {
-        // common case: four in-range samples, none an outlier -> straight-line code
-        const int k0 = 2 * x[i0] - med2, k1 = 2 * x[i0 + 1] - med2, k2 = 2 * x[i0 + 2] - med2,
-                  k3 = 2 * x[i0 + 3] - med2;
-        const uint32_t kmax = static_cast<uint32_t>(max(max(abs(k0), abs(k1)), max(abs(k2), abs(k3))));
-        if (kmax <= dthr) {
-          float4 v;
-          v.x = fast_k(k0);
-          v.y = fast_k(k1);
-          v.z = fast_k(k2);
-          v.w = fast_k(k3);
-          *reinterpret_cast<float4*>(o + i0) = v;
-          continue;
-        }
-      }
-      const int cnt = min(4, n - i0);
-      bool f[4];
-      bool any = false;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        f[e] = (e < cnt) && flagged(i0 + e);
-        any |= f[e];
-      }
-      if (!any && cnt == 4) {   // (kept for the slow path's bookkeeping; the common case returned above)
-        float4 v;
-        v.x = fast_norm(x[i0]);
-        v.y = fast_norm(x[i0 + 1]);
-        v.z = fast_norm(x[i0 + 2]);
-        v.w = fast_norm(x[i0 + 3]);
-        *reinterpret_cast<float4*>(o + i0) = v;
-        continue;
-      }
-      for (int e = 0; e < cnt; ++e) {
-        const int i = i0 + e;
-        if (!f[e]) {
-          o[i] = static_cast<float>(norm_value(x[i], median, denom));
-          continue;
-        }
-        const bool prev_flag = (i > 0) && (e > 0 ? f[e - 1] : flagged(i - 1));
-        if (prev_flag) continue;   // inside a run: the thread at the run start walks it
-        // Walk the run of consecutive outliers starting at i, sequentially, exactly as
-        // riser/preprocess.py:130-138: arr[j-1] is already updated, arr[j+1] is still raw.
-        double prev = (i > 0) ? norm_value(x[i - 1], median, denom) : 0.0;
+      const uint32_t dthr = s.refined;
+      auto flagged = [&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)) > dthr; };
+      // riser/preprocess.py:130-138 for the run of consecutive outliers that starts at i: arr[j-1] is
+      // already updated, arr[j+1] is still raw; the end points of the array are not clipped.
+      auto walk = [&](int i) {
+        double prev = (i > 0) ? quot(2 * x[i - 1] - med2) : 0.0;
         for (int j = i; j < n && flagged(j); ++j) {
           double nv;
           if (j == 0) {
-            nv = (n > 1) ? norm_value(x[1], median, denom) : norm_value(x[0], median, denom);
+            nv = quot(2 * x[n > 1 ? 1 : 0] - med2);
           } else if (j == n - 1) {
             nv = prev;
           } else {
-            nv = clip_outlier(__dmul_rn(__dadd_rn(prev, norm_value(x[j + 1], median, denom)), 0.5));
+            nv = clip_outlier(__dmul_rn(__dadd_rn(prev, quot(2 * x[j + 1] - med2)), 0.5));
           }
           o[j] = static_cast<float>(nv);
           prev = nv;
         }
+      };
+
+      // ---- normalise: 4 samples per thread and step (two 8-byte shared loads realigned by the window's
+      //      phase), 16-byte stores; outlier-run starts are pushed to s.runs
+      const int sh = a & 3;
+      const int16_t* q8 = stage + (a & ~3);
+      // |2x - med2| > dthr  <=>  x > x_hi or x < x_lo (clamped to int16: beyond the type nothing can exceed);
+      // tested for the group's four samples at once on the packed 16-bit halves
+      const int x_hi = min(32767, (med2 + static_cast<int>(dthr)) >> 1);            // floor
+      const int x_lo = max(-32768, (med2 - static_cast<int>(dthr) + 1) >> 1);       // ceil
+      const uint32_t hi2 = (static_cast<uint32_t>(x_hi) & 0xffffu) * 0x10001u;
+      const uint32_t lo2 = (static_cast<uint32_t>(x_lo) & 0xffffu) * 0x10001u;
+      auto group_loop = [&](auto value_of) {
+        for (int gidx = tid; gidx < ((dbg & 4) ? 0 : n_groups); gidx += kThreads) {
+          const int i0 = 4 * gidx;
+          const uint2 lo = *reinterpret_cast<const uint2*>(q8 + i0);
+          const uint2 hi = *reinterpret_cast<const uint2*>(q8 + i0 + 4);
+          const uint32_t wa = (sh & 2) ? lo.y : lo.x, wb = (sh & 2) ? hi.x : lo.y, wc = (sh & 2) ? hi.y : hi.x;
+          const uint32_t p0 = __funnelshift_r(wa, wb, 16 * (sh & 1)), p1 = __funnelshift_r(wb, wc, 16 * (sh & 1));
+          const int xs[4] = {static_cast<int16_t>(p0 & 0xffffu), static_cast<int16_t>(p0 >> 16),
+                             static_cast<int16_t>(p1 & 0xffffu), static_cast<int16_t>(p1 >> 16)};
+          const int cnt = min(4, n - i0);
+          if (cnt == 4) {
+            float4 v;
+            v.x = value_of(xs[0]);
+            v.y = value_of(xs[1]);
+            v.z = value_of(xs[2]);
+            v.w = value_of(xs[3]);
+            if (dbg & 1) {
+              if (v.x == 123.456f) o[i0] = v.y + v.z + v.w;
+            } else {
+              *reinterpret_cast<float4*>(o + i0) = v;
+            }
+          } else {       // tail group: what lies past the window in the staging buffer is not a sample
+            for (int e = 0; e < cnt; ++e) o[i0 + e] = value_of(xs[e]);
+          }
+          if (__vimax3_s16x2(p0, p1, hi2) != hi2 || __vimin3_s16x2(p0, p1, lo2) != lo2) {
+            // rare: some sample of this group is an outlier (or, in the tail group, stale data past the window)
+            bool fprev = (i0 > 0) && flagged(i0 - 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool fe = (e < cnt) && static_cast<uint32_t>(abs(2 * xs[e] - med2)) > dthr;
+              if (fe && !fprev) {
+                const uint32_t pos = atomicAdd(&s.n_runs, 1u);
+                if (pos < static_cast<uint32_t>(kMaxRuns)) s.runs[pos] = i0 + e;
+              }
+              fprev = fe;
+            }
+          }
+        }
+      };
+      if (use_lut) {
+        const float* lutb = lut - vmin;              // indexed by the sample value itself
+        group_loop([&](int xv) { return lutb[xv]; });
+      } else {
+        group_loop([&](int xv) { return static_cast<float>(quot(2 * xv - med2)); });
+      }
+      __syncthreads();   // every sample has its plain quotient; the runs overwrite theirs
+      const uint32_t n_runs = s.n_runs;
+      if (n_runs <= static_cast<uint32_t>(kMaxRuns)) {
+        for (uint32_t r = tid; r < n_runs; r += kThreads) walk(s.runs[r]);
+      } else {             // list overflowed: find the run starts again
+        for (int i = tid; i < n; i += kThreads)
+          if (flagged(i) && !(i > 0 && flagged(i - 1))) walk(i);
       }
     }
     __syncthreads();   // stage / scratch are reused by the next read
@@ -561,7 +681,19 @@ extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int
                 max_len, kMaxLen);
   RISER_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ld_out & 3) == 0 && ld_out >= max_len,
                 "riser_normalise: out must be 16-byte aligned, ld_out a multiple of 4 and >= max_len");
-  const size_t smem = ((sizeof(SelectScratch) + 15) & ~size_t(15)) + 2 * (static_cast<size_t>(max_len) + 16);
+  // staging buffers of whole 16-byte blocks: window + up to 7 samples of phase + tail block, 128-byte pitch
+  const int buf_samples = (max_len + 16 + 63) & ~63;
+  const size_t scratch = (sizeof(SelectScratch) + 127) & ~size_t(127);
+  static int nbuf_env = -1;
+  if (nbuf_env < 0) {
+    const char* e = getenv("RISER_NORM_NBUF");
+    nbuf_env = e ? atoi(e) : 0;
+  }
+  // One staging buffer + L2 prefetch of the next read by default: a second buffer (RISER_NORM_NBUF=2, the next
+  // read's copy in flight during this read's work) costs a resident CTA per SM and measured slower.
+  int nbuf = (nbuf_env == 2) ? 2 : 1;
+  if (scratch + 2 * static_cast<size_t>(nbuf) * buf_samples > 227 * 1024) nbuf = 1;
+  const size_t smem = scratch + 2 * static_cast<size_t>(nbuf) * buf_samples;
   static size_t configured[64] = {0};   // per device
   int dev = 0;
   RISER_CUDA_TRY(cudaGetDevice(&dev));
@@ -573,9 +705,20 @@ extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int
   int per_sm = 0;
   RISER_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normalise_kernel, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
+  // timing experiments (profiles/README.md): RISER_NORM_CTAS caps the resident CTAs per SM; RISER_NORM_DBG is a
+  // bit mask -- 1 no global stores, 2 no histogram atomics, 4 no normalise loop (all three give WRONG results),
+  // 8 per-sample float64 quotients instead of the value look-up table (same results)
+  static int ctas_env = -1, dbg = 0;
+  if (ctas_env < 0) {
+    const char* e = getenv("RISER_NORM_CTAS");
+    ctas_env = e ? atoi(e) : 0;
+    e = getenv("RISER_NORM_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (ctas_env > 0) per_sm = std::min(per_sm, ctas_env);
   const int grid = std::min(B, sm_count() * per_sm);
   normalise_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, start, len, B, out, ld_out,
-                                                               med2_mad4);
+                                                               med2_mad4, nbuf, buf_samples, dbg);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
