@@ -202,7 +202,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from riser_b200 import Kit, SignalProcessor, Model, BatchedClassifier, RaggedBatch, synth, model as rmodel
+    from riser_b200 import Kit, SignalProcessor, Model, BatchedClassifier, RaggedBatch, synth, _lib, model as rmodel
     from riser_b200.config import shipped_config
 
     torch.cuda.set_device(local_rank)
@@ -262,6 +262,20 @@ def main():
     conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / args.steps
     # the bracket covers layer 0 (CUDA cores) + conv layers 1..11; take layer 0's launches out
     conv_ms -= mdl.time_layer0(clf._buffers(B)["x"], length, L)
+    # ---- the HBM-bound stage: riser_normalise alone (6 bytes per sample: int16 in, fp32 out), L2 flushed
+    L_ = _lib.lib()
+    xbuf = clf._buffers(B)["x"]
+    nev = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(L_.riser_normalise(_lib.ptr(batch.sig), _lib.ptr(batch.off), _lib.ptr(start), _lib.ptr(length), B, L,
+                                      _lib.ptr(xbuf), xbuf.stride(0), None, _lib.stream_ptr()), "riser_normalise")
+        b.record()
+        nev.append((a, b))
+    torch.cuda.synchronize()
+    norm_ms = sorted(a.elapsed_time(b) for a, b in nev)[len(nev) // 2]
     # ---- e2e: the public streaming API with HOST buffers.  Every step copies its 131 MB of
     #      pinned int16 input H2D and brings decisions + probabilities back D2H; the copy of
     #      step k+1 overlaps the kernels of step k (FixedBatchPipeline, two slots).
@@ -325,6 +339,10 @@ def main():
                          "executed_note": "fp16-pass-equivalents of tcgen05 work per algorithmic FLOP: 1 (F16), "
                                           "2 (F16_W2), 3 (F16_X3), 2 (F16_F8: one fp16 pass + two e4m3 passes at twice the rate)",
                          "share_of_step": conv_ms / (total_ms / args.steps)},
+            "roofline_normalise": {"bound": "hbm", "kernel": "normalise_kernel", "achieved": 6 * L * B / norm_ms / 1e6,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": 6 * L * B / norm_ms / 1e6 / hbm_peak,
+                                   "ms": norm_ms, "algorithmic_bytes_per_read": 6 * L,
+                                   "peak_source": f"hbm_gbs, {peak_src}"},
             "e2e": {"value": reads / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "overlap": "H2D of step k+1 overlaps kernels of step k (2 slots)"},

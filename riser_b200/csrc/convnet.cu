@@ -381,7 +381,11 @@ __device__ __forceinline__ void epilogue_row16(const uint32_t (&ve)[16], const u
       const float2 back = __half22float2(hv[c]);
       lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
     }
+#ifdef RISER_DBG_TRAFFIC   // timing experiment (wrong results): the lo plane is written over the hi plane
+    uint4* ol = reinterpret_cast<uint4*>(ohi);
+#else
     uint4* ol = reinterpret_cast<uint4*>(ohi + lo_off);
+#endif
     ol[0] = *reinterpret_cast<const uint4*>(lv);
     ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
   }
@@ -1507,8 +1511,13 @@ conv_eo_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__
 #pragma unroll
             for (int ap = 0; ap < PLANES; ++ap) {
               unsigned char* t = dst + (ms * PLANES + ap) * 2 * kEoTile;
-              tma_load_2d(t, &tm_e, &s.a_full[sa], ap * a.cin_p + kb * 32, u0 + ms * kBlockM);              // E[j ..]
-              tma_load_2d(t + kEoTile, &tm_o, &s.a_full[sa], ap * a.cin_p + kb * 32, u0 + ms * kBlockM - 1);  // O[j-1 ..]
+#ifdef RISER_DBG_TRAFFIC   // timing experiment (wrong results): the lo plane is read from the hi plane's bytes
+              const int apc = 0;
+#else
+              const int apc = ap * a.cin_p;
+#endif
+              tma_load_2d(t, &tm_e, &s.a_full[sa], apc + kb * 32, u0 + ms * kBlockM);              // E[j ..]
+              tma_load_2d(t + kEoTile, &tm_o, &s.a_full[sa], apc + kb * 32, u0 + ms * kBlockM - 1);  // O[j-1 ..]
             }
           if (++sa == a.a_stages) {
             sa = 0;

@@ -22,7 +22,7 @@ constexpr int kBins = 2048;             // first-pass histogram bins
 constexpr int kBinsPerThread = kBins / kThreads;
 constexpr int kSubBins = 128;           // refinement pass (shift <= 7)
 constexpr int kMaxLen = 98304;          // samples staged in smem (192 KB)
-constexpr int kMaxRuns = 1024;          // outlier-run start indices collected per read (more: rescan path)
+constexpr int kMaxRuns = 512;           // outlier-run start indices collected per read (more: rescan path)
 
 constexpr double kOutlierLimit = 3.5;   // riser/preprocess.py:6
 constexpr double kScalingFactor = 1.4826;  // riser/preprocess.py:7
@@ -63,28 +63,39 @@ struct StagedWindow {
   int a, n;
   __device__ __forceinline__ int operator[](int i) const { return stage[a + i]; }
   template <class F>
-  __device__ __forceinline__ void for_each(F f) const {
-    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
-    const int end = a + n;
-    const int n_chunks = (end + 7) >> 3;
-    for (int c = threadIdx.x; c < n_chunks; c += kThreads) {
-      const uint4 v = s4[c];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      const int base = 8 * c;
-      if (base >= a && base + 8 <= end) {
+  __device__ __forceinline__ void chunk(int c, int end, F& f) const {
+    const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int base = 8 * c;
+    if (base >= a && base + 8 <= end) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f(static_cast<int>(static_cast<int16_t>(w[j] & 0xffffu)));
-          f(static_cast<int>(static_cast<int16_t>(w[j] >> 16)));
-        }
-      } else {
+      for (int j = 0; j < 4; ++j) {
+        f(static_cast<int>(static_cast<int16_t>(w[j] & 0xffffu)));
+        f(static_cast<int>(static_cast<int16_t>(w[j] >> 16)));
+      }
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int p = base + j;
-          if (p >= a && p < end) f(static_cast<int>(static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu)));
-        }
+      for (int j = 0; j < 8; ++j) {
+        const int p = base + j;
+        if (p >= a && p < end) f(static_cast<int>(static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu)));
       }
     }
+  }
+  // Chunk order: warp w owns the contiguous chunks [w R, (w + 1) R); lane l walks l S .. l S + S - 1 of them with
+  // S odd, so the 16-byte loads of a warp stay bank-conflict free while its lanes work on samples ~8 S apart --
+  // neighbouring samples of a squiggle sit on the same current level, and 32 lanes hitting the same few histogram
+  // bins serialise the shared-memory atomics.  The (< 64) chunks left over per warp are taken lane by lane.
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const {
+    const int end = a + n;
+    const int n_chunks = (end + 7) >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int R = (n_chunks + kWarps - 1) / kWarps;
+    const int c0 = warp * R, c1 = min(c0 + R, n_chunks);
+    int S = (c1 - c0) >> 5;
+    S = (S > 0) ? ((S - 1) | 1) : 0;          // largest odd number <= (c1 - c0) / 32
+    for (int i = 0; i < S; ++i) chunk(c0 + lane * S + i, end, f);
+    for (int c = c0 + 32 * S + lane; c < c1; c += 32) chunk(c, end, f);
   }
 };
 
@@ -193,7 +204,7 @@ __device__ __forceinline__ double clip_outlier(double v) {
 //   normalise + smooth: every sample gets the exact quotient; the starts of outlier runs are collected
 //            in shared memory and walked afterwards, one run per thread, so a rare outlier no longer
 //            stalls its whole warp in a divergent slow path
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
                  const int32_t* __restrict__ start, const int32_t* __restrict__ len, int B,
                  float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ med2_mad4,
@@ -210,11 +221,9 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     fence_mbar_init();
   }
   __syncthreads();
-  // thread 0: bulk copy of read r's window (whole 16-byte blocks) into staging buffer `buf`
-  auto issue = [&](int r, int buf) {
-    const int nr = len[r];
+  // thread 0: bulk copy of a window of nr samples at gr (whole 16-byte blocks) into staging buffer `buf`
+  auto issue = [&](int nr, const int16_t* gr, int buf) {
     if (nr <= 0) return;
-    const int16_t* gr = sig + off[r] + (start ? start[r] : 0);
     const int ar = static_cast<int>((reinterpret_cast<uintptr_t>(gr) >> 1) & 7);
     const uint32_t bytes = static_cast<uint32_t>(((ar + nr + 7) >> 3) << 4);
     mbar_arrive_expect_tx(&s.bar[buf], bytes);
@@ -222,30 +231,38 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
   };
   // one staging buffer: the NEXT read's blocks are pulled into L2 while this one is processed, so that its
   // copy at the top of the next iteration is an L2 hit and the HBM reads spread over the compute phases
-  auto prefetch = [&](int r) {
-    const int nr = len[r];
+  auto prefetch = [&](int nr, const int16_t* gr) {
     if (nr <= 0) return;
-    const int16_t* gr = sig + off[r] + (start ? start[r] : 0);
     const int ar = static_cast<int>((reinterpret_cast<uintptr_t>(gr) >> 1) & 7);
     bulk_prefetch_l2(gr - ar, static_cast<uint32_t>(((ar + nr + 7) >> 3) << 4));
   };
-  if (nbuf == 2 && tid == 0) issue(blockIdx.x, 0);
+  // window length / position of the read being processed and of the CTA's next one (loaded an iteration ahead,
+  // so that no global-load latency sits between the end of a read and the copy of the next)
+  auto meta = [&](int r, int& nr, const int16_t*& gr) {
+    nr = 0;
+    gr = sig;
+    if (r < B) {
+      nr = len[r];
+      gr = sig + off[r] + (start ? start[r] : 0);
+    }
+  };
+  int n_cur, n_nxt;
+  const int16_t *g_cur, *g_nxt;
+  meta(blockIdx.x, n_cur, g_cur);
+  if (nbuf == 2 && tid == 0) issue(n_cur, g_cur, 0);
   uint32_t phase_bits = 0;             // bit `buf` = parity the next wait on bar[buf] uses
 
   int it = 0;
-  for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+  for (int b = blockIdx.x; b < B; b += gridDim.x, ++it, n_cur = n_nxt, g_cur = g_nxt) {
     const int buf = (nbuf == 2) ? (it & 1) : 0;
+    if (tid == 0 && nbuf == 1) issue(n_cur, g_cur, 0);
+    meta(b + gridDim.x, n_nxt, g_nxt);
     if (tid == 0) {
-      if (nbuf == 2) {
-        if (b + static_cast<int>(gridDim.x) < B) issue(b + gridDim.x, buf ^ 1);
-      } else {
-        issue(b, 0);
-        if (b + static_cast<int>(gridDim.x) < B) prefetch(b + gridDim.x);
-      }
+      if (nbuf == 2) issue(n_nxt, g_nxt, buf ^ 1); else prefetch(n_nxt, g_nxt);
     }
-    const int n = len[b];
+    const int n = n_cur;
     if (n <= 0) continue;                 // block-uniform; nothing was issued for this read
-    const int16_t* g = sig + off[b] + (start ? start[b] : 0);
+    const int16_t* g = g_cur;
     float* o = out + static_cast<int64_t>(b) * ld_out;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 1) & 7);
     const int16_t* stage = stage_base + static_cast<size_t>(buf) * buf_samples;
@@ -404,19 +421,27 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       auto flagged = [&](int i) { return static_cast<uint32_t>(abs(2 * x[i] - med2)) > dthr; };
       // riser/preprocess.py:130-138 for the run of consecutive outliers that starts at i: arr[j-1] is
       // already updated, arr[j+1] is still raw; the end points of the array are not clipped.
+      // The recurrence is sequential, and a float64 op has a long dependent latency: per step only ONE fma
+      // (prev / 2 + raw / 2, the same rounding as (prev + raw) / 2) and the clip stay on the chain; the raw
+      // neighbour's quotient and the "is the next sample an outlier" test are computed a step ahead.
       auto walk = [&](int i) {
         double prev = (i > 0) ? quot(2 * x[i - 1] - med2) : 0.0;
-        for (int j = i; j < n && flagged(j); ++j) {
+        double rh_next = 0.5 * quot(2 * x[min(i + 1, n - 1)] - med2);        // raw value of sample j + 1, halved
+        for (int j = i;; ++j) {
+          const double rh = rh_next;
+          const bool more = (j + 1 < n) && flagged(j + 1);
+          if (more) rh_next = 0.5 * quot(2 * x[min(j + 2, n - 1)] - med2);
           double nv;
           if (j == 0) {
-            nv = quot(2 * x[n > 1 ? 1 : 0] - med2);
+            nv = 2.0 * rh;                       // arr[0] = arr[1] (raw)
           } else if (j == n - 1) {
-            nv = prev;
+            nv = prev;                           // arr[n-1] = arr[n-2] (already updated)
           } else {
-            nv = clip_outlier(__dmul_rn(__dadd_rn(prev, quot(2 * x[j + 1] - med2)), 0.5));
+            nv = clip_outlier(__fma_rn(prev, 0.5, rh));
           }
           o[j] = static_cast<float>(nv);
           prev = nv;
+          if (!more) break;
         }
       };
 
@@ -430,8 +455,29 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       const int x_lo = max(-32768, (med2 - static_cast<int>(dthr) + 1) >> 1);       // ceil
       const uint32_t hi2 = (static_cast<uint32_t>(x_hi) & 0xffffu) * 0x10001u;
       const uint32_t lo2 = (static_cast<uint32_t>(x_lo) & 0xffffu) * 0x10001u;
+      // Outlier bookkeeping stays out of the hot loop: a thread only notes WHICH of its groups held an outlier (one
+      // bit per step) and looks at those groups again afterwards, pushing the starts of outlier runs to s.runs.
+      auto note_runs = [&](uint32_t mask, int step0) {
+        while (mask) {
+          const int it_ = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int i0 = 4 * (tid + (step0 + it_) * kThreads);
+          const int cnt = min(4, n - i0);
+          bool fprev = (i0 > 0) && flagged(i0 - 1);
+          for (int e = 0; e < cnt; ++e) {
+            const bool fe = flagged(i0 + e);
+            if (fe && !fprev) {
+              const uint32_t pos = atomicAdd(&s.n_runs, 1u);
+              if (pos < static_cast<uint32_t>(kMaxRuns)) s.runs[pos] = i0 + e;
+            }
+            fprev = fe;
+          }
+        }
+      };
       auto group_loop = [&](auto value_of) {
-        for (int gidx = tid; gidx < ((dbg & 4) ? 0 : n_groups); gidx += kThreads) {
+        uint32_t gmask = 0;
+        int step = 0;
+        for (int gidx = tid; gidx < ((dbg & 4) ? 0 : n_groups); gidx += kThreads, ++step) {
           const int i0 = 4 * gidx;
           const uint2 lo = *reinterpret_cast<const uint2*>(q8 + i0);
           const uint2 hi = *reinterpret_cast<const uint2*>(q8 + i0 + 4);
@@ -442,41 +488,41 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
           const int cnt = min(4, n - i0);
           if (cnt == 4) {
             float4 v;
-            v.x = value_of(xs[0]);
-            v.y = value_of(xs[1]);
-            v.z = value_of(xs[2]);
-            v.w = value_of(xs[3]);
+            v.x = value_of(xs[0], 0);
+            v.y = value_of(xs[1], 1);
+            v.z = value_of(xs[2], 2);
+            v.w = value_of(xs[3], 3);
             if (dbg & 1) {
               if (v.x == 123.456f) o[i0] = v.y + v.z + v.w;
             } else {
               *reinterpret_cast<float4*>(o + i0) = v;
             }
           } else {       // tail group: what lies past the window in the staging buffer is not a sample
-            for (int e = 0; e < cnt; ++e) o[i0 + e] = value_of(xs[e]);
+            for (int e = 0; e < cnt; ++e) o[i0 + e] = value_of(xs[e], 0);
           }
-          if (__vimax3_s16x2(p0, p1, hi2) != hi2 || __vimin3_s16x2(p0, p1, lo2) != lo2) {
-            // rare: some sample of this group is an outlier (or, in the tail group, stale data past the window)
-            bool fprev = (i0 > 0) && flagged(i0 - 1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const bool fe = (e < cnt) && static_cast<uint32_t>(abs(2 * xs[e] - med2)) > dthr;
-              if (fe && !fprev) {
-                const uint32_t pos = atomicAdd(&s.n_runs, 1u);
-                if (pos < static_cast<uint32_t>(kMaxRuns)) s.runs[pos] = i0 + e;
-              }
-              fprev = fe;
-            }
+          // some sample of this group is an outlier (or, in the tail group, stale data past the window)
+          const bool hit = !(dbg & 32) && (__vimax3_s16x2(p0, p1, hi2) != hi2 || __vimin3_s16x2(p0, p1, lo2) != lo2);
+          gmask |= (hit ? 1u : 0u) << (step & 31);
+          if ((step & 31) == 31) {          // windows beyond 32,768 samples: empty the mask every 32 steps
+            note_runs(gmask, step - 31);
+            gmask = 0;
           }
         }
+        note_runs(gmask, step & ~31);
       };
       if (use_lut) {
         const float* lutb = lut - vmin;              // indexed by the sample value itself
-        group_loop([&](int xv) { return lutb[xv]; });
+        if (dbg & 16) {
+          // experiment: samples 0 and 2 of a group from the table, 1 and 3 from the float64 pipe
+          group_loop([&](int xv, int e) { return (e & 1) ? static_cast<float>(quot(2 * xv - med2)) : lutb[xv]; });
+        } else {
+          group_loop([&](int xv, int) { return lutb[xv]; });
+        }
       } else {
-        group_loop([&](int xv) { return static_cast<float>(quot(2 * xv - med2)); });
+        group_loop([&](int xv, int) { return static_cast<float>(quot(2 * xv - med2)); });
       }
       __syncthreads();   // every sample has its plain quotient; the runs overwrite theirs
-      const uint32_t n_runs = s.n_runs;
+      const uint32_t n_runs = (dbg & 64) ? 0u : s.n_runs;
       if (n_runs <= static_cast<uint32_t>(kMaxRuns)) {
         for (uint32_t r = tid; r < n_runs; r += kThreads) walk(s.runs[r]);
       } else {             // list overflowed: find the run starts again
