@@ -167,3 +167,73 @@ def test_retrain_float32_normalise_bit_exact(golden_dir):
     data, dropped = retrain.preprocess_reads(reads, n_secs=2, freq=3012)
     assert data.shape == (4, 6024) and dropped == 2
     assert np.array_equal(data[0], rt.mad_normalise(reads[2][:6024]))
+
+
+def _spiky(rng, n, every, height, base_sd=10.0):
+    x = rng.normal(500, base_sd, size=n)
+    x[::every] += height
+    return np.clip(np.rint(x), -32768, 32767).astype(np.int16)
+
+
+def test_outlier_run_paths(proc):
+    """The run bookkeeping of the normalise kernel: more run starts than the shared-memory list holds (rescan
+    path), with and without the per-value table (range above / below 2048); long runs, runs that touch both ends
+    of the window; windows longer than 32 steps of a thread (> 32,768 samples)."""
+    rng = np.random.default_rng(21)
+    sigs = [
+        _spiky(rng, 12000, 10, 1500),                 # 1200 isolated outliers, table path
+        _spiky(rng, 12000, 10, 3000),                 # the same above the table's range
+        _spiky(rng, 9000, 7, -1200),
+    ]
+    x = rng.normal(480, 12, size=15000)               # long runs, incl. one at each end of the window
+    for a, ln in ((0, 40), (700, 75), (5000, 3), (14960, 40)):
+        x[a:a + ln] += 900
+    sigs.append(np.rint(x).astype(np.int16))
+    x = rng.normal(520, 9, size=70000)                # > 32,768 samples: the per-thread mask is emptied mid-loop
+    idx = rng.choice(70000, size=600, replace=False)
+    x[idx] += rng.choice([-700, 650], size=600)
+    x[40000:40020] -= 800
+    sigs.append(np.rint(x).astype(np.int16))
+    x = rng.normal(500, 6, size=98304)                # the longest window the kernel stages
+    x[rng.random(98304) < 0.004] += 400
+    sigs.append(np.rint(x).astype(np.int16))
+    check_batch(proc, sigs)
+
+
+def test_many_short_reads_with_gaps(proc):
+    """More reads than resident CTAs, zero-length windows in between: the persistent loop's look-ahead
+    (metadata, L2 prefetch) has to stay in step with the reads it skips."""
+    rng = np.random.default_rng(22)
+    B = 3200
+    sigs = [synth.body(rng, int(n)) for n in rng.integers(40, 700, size=B)]
+    start = rng.integers(0, 30, size=B).astype(np.int32)
+    length = np.array([len(s) - st for s, st in zip(sigs, start)], dtype=np.int32)
+    length[rng.random(B) < 0.3] = 0
+    length[:5] = 0
+    length[-3:] = 0
+    check_batch(proc, sigs, start=start, length=length)
+
+
+@pytest.mark.parametrize("env", [{"RISER_NORM_NBUF": "2"}, {"RISER_NORM_DBG": "8"}])
+def test_normalise_kernel_variants(env):
+    """The two opt-in variants (second staging buffer; per-sample float64 quotients instead of the value table)
+    give the same bits.  The switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from riser_b200 import Kit, SignalProcessor, synth\n"
+        "from oracle import preprocess_oracle as pp\n"
+        "proc = SignalProcessor(Kit.create_from_version('RNA002'))\n"
+        "rng = np.random.default_rng(5)\n"
+        "sigs = [synth.body(rng, int(n)) for n in rng.integers(4096, 16000, size=700)]\n"
+        "out, _ = proc.mad_normalise_batch(sigs)\n"
+        "out = out.cpu().numpy()\n"
+        "for b in range(0, 700, 9):\n"
+        "    want = np.asarray(pp.mad_normalise(sigs[b]), dtype=np.float64).astype(np.float32)\n"
+        "    assert np.array_equal(out[b, :len(want)], want), b\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
