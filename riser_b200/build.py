@@ -20,7 +20,20 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+def build_hostpack(force=False):
+    """gcc -> riser_b200/_hostpack<EXT_SUFFIX>: the CPython module that gathers a poll's read prefixes into the
+    pinned staging buffer (csrc/hostpack.c; buffer protocol + pthreads, no third-party headers)."""
+    import sysconfig
+    src = os.path.join(CSRC, "hostpack.c")
+    out = os.path.join(HERE, "_hostpack" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if force or not _newer(out, [src]):
+        subprocess.run([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-pthread", "-I",
+                        sysconfig.get_paths()["include"], src, "-o", out], check=True)
+    return out
+
+
 def build(force=False, verbose=False):
+    build_hostpack(force)
     nvcc = os.environ.get("NVCC", "nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "riser_b200.h"))

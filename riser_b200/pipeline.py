@@ -131,7 +131,16 @@ class BatchedClassifier:
         # size the staging arena once for the longest prefixes the loop can hand over (a read is
         # classified, at the latest, once it exceeds fixed trim + max length: control.py:42-46)
         self._arena.reserve(B * (self.fixed_trim + self.max_len + 8192), B)
-        batch = RaggedBatch(signals, self.device, arena=self._arena)
+        # Upload only what the kernels will look at.  A read whose poly(A) end is cached needs no detection, and its
+        # window is known on the host (control.py:36-56, same integers as select_window_kernel): the max_len samples
+        # after the end -- or nothing, while fewer than min_len samples follow it.  Reads without a cached end go up
+        # whole (detection scans the whole prefix).
+        n_all = np.fromiter((len(s) for s in signals), dtype=np.int64, count=B)
+        has = cached >= 0
+        skip = np.where(has, cached.astype(np.int64) + 1, 0)
+        avail = n_all - skip
+        take = np.where(has, np.where(avail >= self.min_len, np.minimum(avail, self.max_len), 0), n_all)
+        batch = RaggedBatch(signals, self.device, arena=self._arena, skip=skip, take=take, trusted=True)
         start, length, detected = self.select_windows(batch, cached)
         decisions, probs = self.run_windows(batch, start, length, threshold, mode)
         # packed pinned result buffer: len | detected | probs | decisions (4-byte fields first)

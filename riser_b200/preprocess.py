@@ -7,6 +7,8 @@ drops in behind ``SequencerControl``; the additive ``*_batch`` methods are what
 the batched loop (riser_b200/control.py) uses.  All arithmetic that produces
 signal values runs on the GPU; there is no CPU fallback.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -56,34 +58,69 @@ class PinnedArena:
             self.meta_dev = torch.empty(2 * self.meta_capacity + 2, dtype=torch.int64, device=self.device)
 
 
+PACK_THREADS = int(os.environ.get("RISER_PACK_THREADS", max(1, min(4, (os.cpu_count() or 2) // 2))))
+_hostpack_mod = None
+
+
+def _hostpack():
+    """The native gather of read prefixes (csrc/hostpack.c), loaded on first use like the CUDA library; there
+    is no Python fallback."""
+    global _hostpack_mod
+    if _hostpack_mod is None:
+        try:
+            from . import _hostpack as mod
+        except ImportError as e:
+            raise RuntimeError("riser_b200/_hostpack is not built: run `python -m riser_b200.build`") from e
+        _hostpack_mod = mod
+    return _hostpack_mod
+
+
 class RaggedBatch:
     """int16 reads packed back to back on the device: ``sig`` [total], ``off`` int64
     [B+1], ``n`` int32 [B].  Built from host arrays through one pinned staging
-    buffer and one H2D copy (two with metadata); pass a ``PinnedArena`` to reuse buffers."""
-    def __init__(self, signals, device, arena=None):
+    buffer and one H2D copy (two with metadata); pass a ``PinnedArena`` to reuse buffers.
+
+    The gather into the staging buffer is done by the native ``_hostpack`` module (buffer protocol +
+    threads, csrc/hostpack.c).  ``skip`` / ``take`` (int64 sample counts per read, optional) upload only
+    ``signal[skip:skip+take]`` of a read; ``off`` then holds the VIRTUAL start of the read (packed position
+    - skip), so that ``sig[off[b] + i]`` is still sample i of read b for every i inside the uploaded slice
+    and the kernels need not know.  ``n`` is always the full prefix length.
+    ``trusted=True`` skips the per-read dtype / contiguity check (the live loop's arrays come straight from
+    ``np.frombuffer(raw_data, int16)``)."""
+    def __init__(self, signals, device, arena=None, skip=None, take=None, trusted=False):
         B = len(signals)
-        n = np.fromiter((len(s) for s in signals), dtype=np.int64, count=B)
-        # keep every read 16-byte aligned so the kernels' vector loads need no peeling
-        padded = (n + 7) & ~7
-        off = np.zeros(B + 1, dtype=np.int64)
-        np.cumsum(padded, out=off[1:])
-        total = int(off[-1]) + 8
+        if not trusted:
+            signals = [np.ascontiguousarray(s, dtype=np.int16) for s in signals]
+        nbytes = np.zeros(B, dtype=np.int64)
+        hp = _hostpack()
+        hp.lengths(signals, nbytes)
+        n = nbytes >> 1
+        if take is None:
+            skip = np.zeros(B, dtype=np.int64)
+            take = n
+        else:
+            skip = np.ascontiguousarray(skip, dtype=np.int64)
+            take = np.ascontiguousarray(take, dtype=np.int64)
+        # keep every packed read 16-byte aligned so the kernels' vector loads need no peeling
+        padded = (take + 7) & ~7
+        pos = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(padded, out=pos[1:])
+        total = int(pos[-1]) + 8
+        off = pos.copy()
+        off[:B] -= skip
         self.B = B
         self.n_host = n.astype(np.int32)
+        byte_pos = np.ascontiguousarray(pos[:B] << 1)
         if arena is None:
             host = torch.empty(total, dtype=torch.int16).pin_memory()
-            hv = host.numpy()
-            for s, o, k in zip(signals, off[:-1], n):
-                hv[o:o + k] = s
+            hp.pack(signals, host.numpy(), byte_pos, skip << 1, take << 1, PACK_THREADS)
             self.sig = host.to(device, non_blocking=True)
             self.off = torch.from_numpy(off).to(device, non_blocking=True)
             self.n = torch.from_numpy(self.n_host).to(device, non_blocking=True)
             self._host = host      # keep the pinned buffer alive until the copy has run
         else:
             arena.reserve(total, B)
-            hv = arena.host.numpy()
-            for s, o, k in zip(signals, off[:-1], n):
-                hv[o:o + k] = s
+            hp.pack(signals, arena.host.numpy(), byte_pos, skip << 1, take << 1, PACK_THREADS)
             self.sig = arena.dev[:total]
             self.sig.copy_(arena.host[:total], non_blocking=True)
             mh = arena.meta_host.numpy()
