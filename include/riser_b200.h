@@ -87,6 +87,10 @@ int riser_normalise_max_len(void);
  * i >= len[b] of the row are not written.  len[b] == 0 writes nothing.
  * mad == 0 writes zeros (preprocess.py:122-124).
  * out must be 16-byte aligned and ld_out a multiple of 4.
+ * The window is staged by a bulk copy of whole 16-byte blocks: the sig allocation must
+ * reach the end of the 16-byte block that holds a window's last sample (any cudaMalloc'd
+ * buffer does).  off[b] may be a VIRTUAL start (the caller uploaded only part of read b),
+ * as long as [off[b] + start[b], off[b] + start[b] + len[b]) lies inside the allocation.
  * med2_mad4 (optional, may be NULL): int32 [B,2] = {2*median, 4*MAD} (exact).  */
 int riser_normalise(const int16_t* sig, const int64_t* off, const int32_t* start,
                     const int32_t* len, int B, int max_len, float* out, int64_t ld_out,
