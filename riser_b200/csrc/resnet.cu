@@ -1,13 +1,17 @@
 // ResNet variant of the classifier (riser/nets/resnet.py).
 // The reference ships no config or weights for it (train-only, hyper-parameters unpinned) and
-// plausible configurations are 25k-130k parameters, so this round it runs as generic fp32
-// direct convolutions on CUDA cores: channel-last activations, BatchNorm folded into the
-// weights on the host, residual add + ReLU fused into the convolution, per-read lengths so
-// that ragged batches give per-read results.  A tcgen05 path is left for a later round.
+// plausible configurations are 25k-130k parameters, so it runs as fp32 convolutions on CUDA cores:
+// channel-last activations, BatchNorm folded into the weights on the host, residual add + ReLU fused
+// into the convolution, per-read lengths so that ragged batches give per-read results.  The
+// convolution is register-tiled (weights of a channel tile and the input rows of a position tile in
+// shared memory, 8 positions x 4 channels of accumulators per thread); the per-element kernel it
+// replaced is kept for shapes whose tiles do not fit shared memory.  A tcgen05 path is left for a
+// later round.
 #include "common.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <stdlib.h>
 
 namespace riser {
 namespace {
@@ -40,6 +44,83 @@ conv1d_cl_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_i
     }
     if (residual) acc += residual[idx];
     out[idx] = relu ? fmaxf(acc, 0.f) : acc;
+  }
+}
+
+// The same convolution, register-tiled: a CTA computes a tile of TYP = TY * PT output positions x CT output
+// channels of one read.  The weights of the channel tile ([K][Cin][CT], zero-padded) and the input rows the tile
+// touches are staged in shared memory once; thread (tx, ty) keeps PT positions x 4 channels of accumulators and
+// per (tap, input channel) does one 16-byte weight load, PT input loads (warp broadcasts) and 4 PT FMAs.
+// Geometry (TX = CT / 4, TY = 256 / TX) is chosen on the host; rows outside [0, len_in) are staged as zeros.
+template <int PT>
+__global__ void __launch_bounds__(256)
+conv1d_cl_tiled_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_in,
+                       const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ residual, float* __restrict__ out,
+                       const int32_t* __restrict__ len_out, int Lin_pad, int Lout_pad, int Cin, int Cout,
+                       int K, int stride, int pad, int relu, int CT, int TX, int TY, int pitch) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int b = blockIdx.z;
+  const int co0 = blockIdx.y * CT;
+  const int TYP = TY * PT;
+  const int t0 = blockIdx.x * TYP;
+  const int Lo = len_out[b];
+  if (t0 >= Lo) return;                               // nothing of this tile is written
+  const int Lb = len_in[b];
+  const int rows = (TYP - 1) * stride + K;
+  float* w_s = smem_f;                                // [K * Cin][CT]
+  float* in_s = smem_f + ((K * Cin * CT + 3) & ~3);   // [rows][pitch]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * Cin * CT; i += 256) {
+    const int c = i % CT, kc = i / CT;
+    w_s[i] = (co0 + c < Cout) ? __ldg(w + static_cast<int64_t>(kc) * Cout + co0 + c) : 0.f;
+  }
+  const int ti0 = t0 * stride - pad;
+  const float* inb = in + static_cast<int64_t>(b) * Lin_pad * Cin;
+  for (int i = tid; i < rows * Cin; i += 256) {
+    const int r = i / Cin, ci = i - r * Cin;
+    const int ti = ti0 + r;
+    in_s[r * pitch + ci] = (ti >= 0 && ti < Lb) ? __ldg(inb + static_cast<int64_t>(ti) * Cin + ci) : 0.f;
+  }
+  __syncthreads();
+  const int tx = tid % TX, ty = tid / TX;
+  if (ty >= TY) return;
+  float acc[PT][4];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+  const float* a_base = in_s + ty * PT * stride * pitch;
+  const float* w_base = w_s + 4 * tx;
+  for (int k = 0; k < K; ++k) {
+    const float* a_k = a_base + k * pitch;
+    const float* w_k = w_base + static_cast<size_t>(k) * Cin * CT;
+#pragma unroll 4
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float4 wv = *reinterpret_cast<const float4*>(w_k + ci * CT);
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        const float a = a_k[p * stride * pitch + ci];
+        acc[p][0] = fmaf(a, wv.x, acc[p][0]);
+        acc[p][1] = fmaf(a, wv.y, acc[p][1]);
+        acc[p][2] = fmaf(a, wv.z, acc[p][2]);
+        acc[p][3] = fmaf(a, wv.w, acc[p][3]);
+      }
+    }
+  }
+  const int c0 = co0 + 4 * tx;
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    const int t = t0 + ty * PT + p;
+    if (t >= Lo) break;
+    const int64_t o = (static_cast<int64_t>(b) * Lout_pad + t) * Cout + c0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c0 + c >= Cout) break;
+      float v = acc[p][c] + __ldg(bias + c0 + c);
+      if (residual) v += residual[o + c];
+      out[o + c] = relu ? fmaxf(v, 0.f) : v;
+    }
   }
 }
 
@@ -103,6 +184,25 @@ gap_linear_softmax_kernel(const float* __restrict__ in, const int32_t* __restric
   }
 }
 
+// Valid lengths after every op of the network's main chain, from the input lengths: op j is Conv1d(k, stride, pad)
+// (floor((n + 2 pad - k) / stride) + 1, clamped at 0) or, k < 0, MaxPool1d(2, 2, padding 1) (n / 2 + 1; 0 stays 0).
+__global__ void len_chain_kernel(const int32_t* __restrict__ len0, int B, const int32_t* __restrict__ ksp, int n_ops,
+                                 int32_t* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = len0[b];
+  for (int j = 0; j < n_ops; ++j) {
+    const int k = ksp[3 * j], st = ksp[3 * j + 1], pd = ksp[3 * j + 2];
+    if (k < 0) {
+      n = n > 0 ? n / 2 + 1 : 0;
+    } else {
+      const int num = n + 2 * pd - k;
+      n = num >= 0 ? num / st + 1 : 0;
+    }
+    out[static_cast<int64_t>(j) * B + b] = n;
+  }
+}
+
 int grid_for(int64_t total) { return static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16)); }
 
 }  // namespace
@@ -117,6 +217,33 @@ extern "C" int riser_conv1d_cl(const float* in, const int32_t* len_in, const flo
   RISER_REQUIRE(in && len_in && w && bias && out && len_out, "riser_conv1d_cl: null pointer");
   RISER_REQUIRE(B > 0 && Lin_pad > 0 && Lout_pad > 0 && Cin > 0 && Cout > 0 && K > 0 && stride > 0 && pad >= 0,
                 "riser_conv1d_cl: bad shape");
+  // register-tiled kernel whenever its weight tile and input rows fit shared memory (every ResNet shape does)
+  {
+    constexpr int PT = 8;
+    // channel tile: all output channels when <= 128 (a 67-channel layer must not pay for a second, almost empty tile)
+    const int c4 = (Cout + 3) & ~3;
+    const int CT = c4 <= 128 ? c4 : 64;
+    const int TX = CT / 4, TY = 256 / TX, TYP = TY * PT;
+    const int pitch = Cin | 1;                                    // odd row pitch: the ty's of a warp hit distinct banks
+    const int rows = (TYP - 1) * stride + K;
+    const size_t smem = (static_cast<size_t>((K * Cin * CT + 3) & ~3) + static_cast<size_t>(rows) * pitch) * sizeof(float);
+    if (smem <= 200 * 1024 && B <= 65535 && !getenv("RISER_RESNET_NAIVE")) {
+      static size_t configured[64] = {0};
+      int dev = 0;
+      RISER_CUDA_TRY(cudaGetDevice(&dev));
+      if (smem > configured[dev & 63]) {
+        RISER_CUDA_TRY(cudaFuncSetAttribute(conv1d_cl_tiled_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        configured[dev & 63] = smem;
+      }
+      const dim3 grid((Lout_pad + TYP - 1) / TYP, (Cout + CT - 1) / CT, B);
+      conv1d_cl_tiled_kernel<PT><<<grid, 256, smem, as_stream(stream)>>>(in, len_in, w, bias, residual, out, len_out,
+                                                                         Lin_pad, Lout_pad, Cin, Cout, K, stride, pad,
+                                                                         relu, CT, TX, TY, pitch);
+      RISER_CUDA_TRY(cudaGetLastError());
+      return RISER_OK;
+    }
+  }
   const int64_t total = static_cast<int64_t>(B) * Lout_pad * Cout;
   conv1d_cl_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(in, len_in, w, bias, residual, out, len_out, B,
                                                                   Lin_pad, Lout_pad, Cin, Cout, K, stride, pad, relu);
@@ -139,6 +266,16 @@ extern "C" int riser_gap_linear_softmax(const float* in, const int32_t* len, con
   RISER_REQUIRE(in && len && fc_w && fc_b && probs, "riser_gap_linear_softmax: null pointer");
   RISER_REQUIRE(C <= 1024 && n_classes <= 32 && n_classes >= 1, "riser_gap_linear_softmax: C <= 1024, n_classes <= 32");
   gap_linear_softmax_kernel<<<B, 128, 0, as_stream(stream)>>>(in, len, fc_w, fc_b, probs, B, L_pad, C, n_classes);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+extern "C" int riser_len_chain(const int32_t* len0, int B, const int32_t* ksp, int n_ops, int32_t* out,
+                               riser_stream_t stream) {
+  RISER_REQUIRE(B >= 0 && n_ops >= 0, "riser_len_chain: negative size");
+  if (B == 0 || n_ops == 0) return RISER_OK;
+  RISER_REQUIRE(len0 && ksp && out, "riser_len_chain: null pointer");
+  len_chain_kernel<<<(B + 255) / 256, 256, 0, as_stream(stream)>>>(len0, B, ksp, n_ops, out);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

@@ -78,40 +78,62 @@ class ResNetModel():
         self.fc_w = sd["decoder.2.weight"].contiguous().to(dev)
         self.fc_b = sd["decoder.2.bias"].contiguous().to(dev)
         self.c_last = cin
+        self._acts = {}
+        # (kernel, stride, padding) of every op of the main chain, kernel < 0 = the stem's max-pool (riser_len_chain)
+        chain = [(self.stem.k, self.stem.stride, self.stem.pad), (-1, 2, 1)]
+        for convs, _ in self.blocks:
+            chain += [(cv.k, cv.stride, cv.pad) for cv in convs]
+        self.n_chain = len(chain)
+        self.chain = torch.tensor(chain, dtype=torch.int32).contiguous().to(dev)
 
     # ------------------------------------------------------------------ launches
-    def _conv(self, cv, x, n_in, L_in, residual=None, relu=True):
+    def _buf(self, key, *shape):
+        # rows at or beyond a read's length are never read by any kernel (each takes the per-read lengths), so the
+        # activation buffers need no clearing and are reused from call to call
+        t = self._acts.get((key,) + shape)
+        if t is None:
+            t = self._acts[(key,) + shape] = torch.empty(*shape, dtype=torch.float32, device=self.device)
+        return t
+
+    def _conv(self, cv, x, n_in, L_in, n_out, residual=None, relu=True):
         B = x.shape[0]
-        n_out = cv.out_len(n_in)
         L_out = max(1, (L_in + 2 * cv.pad - cv.k) // cv.stride + 1)
-        out = torch.zeros(B, L_out, cv.cout, dtype=torch.float32, device=self.device)
+        out = self._buf(id(cv), B, L_out, cv.cout)
         _lib.check(_lib.lib().riser_conv1d_cl(_lib.ptr(x), _lib.ptr(n_in), _lib.ptr(cv.w), _lib.ptr(cv.b),
                                               _lib.ptr(residual), _lib.ptr(out), _lib.ptr(n_out), B, L_in, L_out,
                                               cv.cin, cv.cout, cv.k, cv.stride, cv.pad, 1 if relu else 0,
                                               _lib.stream_ptr()), "riser_conv1d_cl")
-        return out, n_out, L_out
+        return out, L_out
 
     def classify_batch(self, x, lens, max_len=None, probs=None, **_unused):
         """x: fp32 [B, ld] normalised signals on the device, lens int32 [B].  -> probs [B, n_classes]."""
         B = x.shape[0]
         L0 = int(max_len if max_len is not None else x.shape[1])
         xin = x[:, :L0].contiguous().view(B, L0, 1)
-        h, n, L = self._conv(self.stem, xin, lens.to(torch.int32), L0)
-        n_p = (n // 2 + 1).to(torch.int32)                                 # MaxPool1d(2, 2, padding=1)
-        n_p = torch.where(n > 0, n_p, torch.zeros_like(n_p))
-        L_p = L // 2 + 1
-        pooled = torch.zeros(B, L_p, self.stem.cout, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().riser_maxpool1d_cl(_lib.ptr(h), _lib.ptr(n), _lib.ptr(pooled), _lib.ptr(n_p), B, L,
-                                                 L_p, self.stem.cout, _lib.stream_ptr()), "riser_maxpool1d_cl")
-        h, n, L = pooled, n_p, L_p
+        lens = lens.to(torch.int32)
+        # valid lengths after every op of the main chain, one launch (stem conv, stem pool, every block conv)
+        n_all = self._acts.get(("len", B))
+        if n_all is None:
+            n_all = self._acts[("len", B)] = torch.empty(self.n_chain, B, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().riser_len_chain(_lib.ptr(lens), B, _lib.ptr(self.chain), self.n_chain, _lib.ptr(n_all),
+                                              _lib.stream_ptr()), "riser_len_chain")
+        h, L = self._conv(self.stem, xin, lens, L0, n_all[0])
+        L_p = L // 2 + 1                                                   # MaxPool1d(2, 2, padding=1)
+        pooled = self._buf("pool", B, L_p, self.stem.cout)
+        _lib.check(_lib.lib().riser_maxpool1d_cl(_lib.ptr(h), _lib.ptr(n_all[0]), _lib.ptr(pooled), _lib.ptr(n_all[1]),
+                                                 B, L, L_p, self.stem.cout, _lib.stream_ptr()), "riser_maxpool1d_cl")
+        h, n, L, j = pooled, n_all[1], L_p, 2
         for convs, shortcut in self.blocks:
+            n_block = n_all[j + len(convs) - 1]             # the shortcut's output is as long as the block's
             res = h
             if shortcut is not None:
-                res, _, _ = self._conv(shortcut, h, n, L, relu=False)
+                res, _ = self._conv(shortcut, h, n, L, n_block, relu=False)
             y, ny, Ly = h, n, L
             for k, cv in enumerate(convs):
                 last = k == len(convs) - 1
-                y, ny, Ly = self._conv(cv, y, ny, Ly, residual=res if last else None, relu=True)
+                y, Ly = self._conv(cv, y, ny, Ly, n_all[j], residual=res if last else None, relu=True)
+                ny = n_all[j]
+                j += 1
             h, n, L = y, ny, Ly
         if probs is None:
             probs = torch.empty(B, self.n_classes, dtype=torch.float32, device=self.device)
