@@ -133,8 +133,10 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reads(sample_reads, length, seed=4321):
+    """The CPU legs' reads: a pool of 256 synthetic chunks repeated (as the GPU batch repeats its pool of 512)."""
     from riser_b200 import synth
-    return synth.body_batch(seed, sample_reads, length)
+    pool = synth.body_batch(seed, min(sample_reads, 256), length)
+    return [pool[i % len(pool)] for i in range(sample_reads)]
 
 
 def time_cpu_path(X, state, threads):
@@ -201,8 +203,8 @@ def main():
     ap.add_argument("--length", type=int, default=LENGTH)
     ap.add_argument("--precision", type=int, default=None, help="0 F16, 1 F16_W2, 2 F16_X3, 3 F16_F8; default = riser_b200.model.DEFAULT_PRECISION")
     ap.add_argument("--chunk", type=int, default=None)
-    ap.add_argument("--ref-reads", type=int, default=48)
-    ap.add_argument("--cpu-sample", type=int, default=96)
+    ap.add_argument("--ref-reads", type=int, default=1024, help="reads per step of the --impl reference arm (~2.6 s of CPU work)")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="reads of the cpu_baseline leg (default: the whole batch, ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -338,11 +340,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f16 operands, f32 accumulate", 1: "f16 (weights hi+lo), f32 accumulate",
-                      2: "f16 hi+lo split (3 tcgen05 passes), f32 accumulate",
-                      3: "f16 pass + e4m3 correction pass (hi+lo split, 2 pass-equivalents), f32 accumulate"}[precision],
+            "dtype": {0: "f16", 1: "f16", 2: "f16", 3: "f16+e4m3"}[precision],
             "data": "synthetic",
-            "config": {"workload": workload_name(B, L), "precision_mode": precision, "chunk": clf.chunk,
+            "config": {"workload": workload_name(B, L), "precision_mode": precision,
+                       "arithmetic": {0: "f16 operands, f32 accumulate (1 tcgen05 pass)",
+                                      1: "f16, weights split hi+lo (2 passes), f32 accumulate",
+                                      2: "f16, weights and activations split hi+lo (3 passes), f32 accumulate",
+                                      3: "f16 pass + e4m3 correction pass carrying the hi/lo terms (2 pass-equivalents; "
+                                         "layers 1-5 as mode 2), f32 accumulate; layer 0 and the head in f32, "
+                                         "normalise in f64"}[precision],
+                       "chunk": clf.chunk,
                        "cache": "L2 flushed between steps (256 MiB write); inputs 393 MB > L2",
                        "flops_per_read": flops_per_read(L), "decisions_made": n_dec},
             "roofline": {"bound": "tensor", "kernel": "fused01_kernel + conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
