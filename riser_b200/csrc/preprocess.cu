@@ -539,7 +539,9 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
 
 constexpr int kRes = 500;               // _TRIM_RESOLUTION, riser/preprocess.py:10
 constexpr int kPerLane = (kRes + 31) / 32;   // 16
-constexpr int kMaxWindows = 1024;       // windows per read (512,000 samples; the live path stops near 18,500)
+constexpr int kMaxWindows = 512;        // windows per read (256,000 samples; the live path stops near 18,500)
+constexpr int kPolyaThreads = 128;      // 4 warps per read: an 18,000-sample prefix has 36 windows, 9 per warp
+constexpr int kPolyaWarps = kPolyaThreads / 32;
 constexpr int kWinBins = 1024;          // value range a window's shared-memory histogram covers
 constexpr int kWinHist = 33 * 32 + 32;  // per-warp histogram storage: 32 lanes x (odd) segment of up to 33 bins
 
@@ -645,33 +647,45 @@ __device__ __forceinline__ void warp_hist_stats(const int (&v)[kPerLane], const 
   __syncwarp();                             // h is cleared again for the warp's next window
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPolyaThreads)
 polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
              const int32_t* __restrict__ nsamp, int B, int32_t* __restrict__ polya_end,
              int32_t* __restrict__ polya_start, int32_t* __restrict__ stats, int max_windows) {
   __shared__ int32_t w_sum[kMaxWindows];
   __shared__ int32_t w_mad4[kMaxWindows];
-  __shared__ __align__(16) uint32_t w_hist[kWarps][kWinHist];
+  __shared__ __align__(16) uint32_t w_hist[kPolyaWarps][kWinHist];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int n = nsamp[b];
     const int16_t* g = sig + off[b];
     const int nw = min(n / kRes, kMaxWindows);
-    for (int w = warp; w < nw; w += kWarps) {
+    // 4-byte loads when the read is 4-byte aligned (a window is 1,000 bytes): a lane takes sample pairs -- which lane
+    // holds which sample is irrelevant to the statistics -- and the NEXT window of this warp is fetched while the
+    // current one is worked on
+    const bool al4 = (reinterpret_cast<uintptr_t>(g) & 3) == 0;
+    uint32_t raw[kPerLane / 2];
+    auto fetch = [&](int w) {
+      const uint32_t* wp2 = reinterpret_cast<const uint32_t*>(g + w * kRes);
+#pragma unroll
+      for (int j = 0; j < kPerLane / 2; ++j) {
+        const int idx = j * 32 + lane;
+        raw[j] = (idx < kRes / 2) ? __ldg(wp2 + idx) : 0u;
+      }
+    };
+    if (al4 && warp < nw) fetch(warp);
+    for (int w = warp; w < nw; w += kPolyaWarps) {
       const int16_t* wp = g + w * kRes;
       int v[kPerLane];
       int sum = 0, vmin = 32767, vmax = -32768;
       bool ok[kPerLane];
-      if ((reinterpret_cast<uintptr_t>(wp) & 3) == 0) {      // 4-byte loads: lane takes sample pairs (which lane holds
-        const uint32_t* wp2 = reinterpret_cast<const uint32_t*>(wp);   // which sample is irrelevant to the statistics)
+      if (al4) {
 #pragma unroll
         for (int j = 0; j < kPerLane / 2; ++j) {
-          const int idx = j * 32 + lane;
-          ok[2 * j] = ok[2 * j + 1] = idx < kRes / 2;
-          const uint32_t pr = ok[2 * j] ? __ldg(wp2 + idx) : 0u;
-          v[2 * j] = static_cast<int16_t>(pr & 0xffffu);
-          v[2 * j + 1] = static_cast<int16_t>(pr >> 16);
+          ok[2 * j] = ok[2 * j + 1] = (j * 32 + lane) < kRes / 2;
+          v[2 * j] = static_cast<int16_t>(raw[j] & 0xffffu);
+          v[2 * j + 1] = static_cast<int16_t>(raw[j] >> 16);
         }
+        if (w + kPolyaWarps < nw) fetch(w + kPolyaWarps);
       } else {
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j) {
@@ -729,23 +743,39 @@ polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      // riser/preprocess.py:45-72.  0 doubles as "unset" exactly like Python truthiness.
+    if (warp == 0) {
+      // riser/preprocess.py:45-72.  0 doubles as "unset" exactly like Python truthiness.  The per-window tests
+      // (three float64 divides each) are independent, so the lanes evaluate 32 windows at a time and the two-state
+      // scan runs on the ballots: start = first window > 0 with mean_change > 20 and mad <= 20; end = first window
+      // after it with mad > 20.
       int pstart = 0, pend = 0;
-      for (int w = 0; w < nw; ++w) {
-        const int i = w * kRes;
-        const double mean = __ddiv_rn(static_cast<double>(w_sum[w]), static_cast<double>(kRes));
-        double rolling = mean;
-        if (i > 2 * kRes)
-          rolling = __ddiv_rn(static_cast<double>(w_sum[w - 2] + w_sum[w - 1]),
-                              static_cast<double>(2 * kRes));
-        const double change = __dmul_rn(__ddiv_rn(__dsub_rn(mean, rolling), rolling), 100.0);
-        const double mad = static_cast<double>(w_mad4[w]) * 0.25;
-        if (pstart == 0 && change > 20.0 && mad <= 20.0) pstart = i;
-        if (pstart != 0 && pend == 0 && mad > 20.0) pend = i;
+      for (int w0 = 0; w0 < nw && pend == 0; w0 += 32) {
+        const int w = w0 + lane;
+        bool cs = false, ce = false;
+        if (w < nw) {
+          const double mean = __ddiv_rn(static_cast<double>(w_sum[w]), static_cast<double>(kRes));
+          double rolling = mean;
+          if (w > 2)
+            rolling = __ddiv_rn(static_cast<double>(w_sum[w - 2] + w_sum[w - 1]),
+                                static_cast<double>(2 * kRes));
+          const double change = __dmul_rn(__ddiv_rn(__dsub_rn(mean, rolling), rolling), 100.0);
+          const double mad = static_cast<double>(w_mad4[w]) * 0.25;
+          cs = w > 0 && change > 20.0 && mad <= 20.0;
+          ce = mad > 20.0;
+        }
+        const uint32_t ms = __ballot_sync(0xffffffffu, cs);
+        uint32_t me = __ballot_sync(0xffffffffu, ce);
+        if (pstart == 0 && ms) pstart = (w0 + __ffs(ms) - 1) * kRes;
+        if (pstart != 0) {
+          const int ws = pstart / kRes - w0;            // start window relative to this chunk (< 0: earlier chunk)
+          if (ws > 0) me &= ~((1u << ws) - 1u);
+          if (me) pend = (w0 + __ffs(me) - 1) * kRes;
+        }
       }
-      polya_end[b] = pend ? pend : -1;
-      if (polya_start) polya_start[b] = pstart ? pstart : -1;
+      if (lane == 0) {
+        polya_end[b] = pend ? pend : -1;
+        if (polya_start) polya_start[b] = pstart ? pstart : -1;
+      }
     }
     __syncthreads();
   }
@@ -875,8 +905,10 @@ extern "C" int riser_polya_end(const int16_t* sig, const int64_t* off, const int
   if (B == 0) return RISER_OK;
   RISER_REQUIRE(sig && off && n && polya_end, "riser_polya_end: null pointer");
   RISER_REQUIRE(!stats || max_windows > 0, "riser_polya_end: stats given but max_windows <= 0");
-  const int grid = std::min(B, sm_count() * 4);
-  polya_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(sig, off, n, B, polya_end, polya_start, stats, max_windows);
+  int per_sm = 0;
+  RISER_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, polya_kernel, kPolyaThreads, 0));
+  const int grid = std::min(B, sm_count() * std::max(per_sm, 1));
+  polya_kernel<<<grid, kPolyaThreads, 0, as_stream(stream)>>>(sig, off, n, B, polya_end, polya_start, stats, max_windows);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }
