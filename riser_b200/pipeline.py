@@ -6,6 +6,8 @@ Everything between the H2D copy of the packed int16 signals and the D2H copy of 
 decision bytes / probabilities runs in the sm_100a kernels behind the C ABI, on the
 current CUDA stream, with one host synchronisation per batch.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -54,6 +56,8 @@ class BatchedClassifier:
         self.ld = (self.max_len + 3) & ~3
         self._bufs = {}
         self._arena = PinnedArena(self.device)
+        self._graphs = {}
+        self.use_graphs = os.environ.get("RISER_LIVE_GRAPHS", "1") != "0"
 
     # ------------------------------------------------------------------ device stages
     def _buffers(self, B):
@@ -88,11 +92,12 @@ class BatchedClassifier:
 
     def select_windows(self, batch, cached_end):
         """poly(A) detection for reads without a cached end + control.py:36-60 gating.
-        cached_end: int32 host array [B] (-1 = not cached).  Device tensors out."""
+        cached_end: int32 [B] (-1 = not cached), host array or device tensor.  Device tensors out."""
         B = batch.B
         buf = self._buffers(B)
         L = _lib.lib()
-        cached = torch.from_numpy(np.ascontiguousarray(cached_end, dtype=np.int32)).to(self.device, non_blocking=True)
+        cached = cached_end if torch.is_tensor(cached_end) else torch.from_numpy(
+            np.ascontiguousarray(cached_end, dtype=np.int32)).to(self.device, non_blocking=True)
         # detection is only needed where nothing is cached; reads with a cache hit keep -1
         # (their prefix is skipped by giving them length 0 in the detection launch)
         n_detect = torch.where(cached >= 0, torch.zeros_like(batch.n), batch.n)
@@ -140,17 +145,40 @@ class BatchedClassifier:
         skip = np.where(has, cached.astype(np.int64) + 1, 0)
         avail = n_all - skip
         take = np.where(has, np.where(avail >= self.min_len, np.minimum(avail, self.max_len), 0), n_all)
-        batch = RaggedBatch(signals, self.device, arena=self._arena, skip=skip, take=take, trusted=True)
-        start, length, detected = self.select_windows(batch, cached)
-        decisions, probs = self.run_windows(batch, start, length, threshold, mode)
+        batch = RaggedBatch(signals, self.device, arena=self._arena, skip=skip, take=take, trusted=True,
+                            extra_i32=cached)
         # packed pinned result buffer: len | detected | probs | decisions (4-byte fields first)
         buf = self._buffers(B)
         host = buf["out_host"]
         o0, o1, o2 = 4 * B, 8 * B, 8 * B + 8 * M * B
-        host[:o0].view(torch.int32).copy_(length, non_blocking=True)
-        host[o0:o1].view(torch.int32).copy_(detected, non_blocking=True)
-        host[o1:o2].view(torch.float32).view(M, B, 2).copy_(probs, non_blocking=True)
-        host[o2:].copy_(decisions, non_blocking=True)
+
+        def device_stage():
+            start, length, detected = self.select_windows(batch, batch.extra)
+            decisions, probs = self.run_windows(batch, start, length, threshold, mode)
+            host[:o0].view(torch.int32).copy_(length, non_blocking=True)
+            host[o0:o1].view(torch.int32).copy_(detected, non_blocking=True)
+            host[o1:o2].view(torch.float32).view(M, B, 2).copy_(probs, non_blocking=True)
+            host[o2:].copy_(decisions, non_blocking=True)
+
+        # Everything between the H2D copies and the host synchronisation is the same kernel sequence on the same
+        # buffers for every poll of a batch-size bucket (the arena, the metadata block and the per-bucket buffers
+        # keep their addresses; ragged lengths live in device memory): it is captured into a CUDA graph the second
+        # time a bucket is seen and replayed from then on -- one launch instead of ~20 per model.
+        key = (B, float(threshold), mode, self._arena.generation)
+        state = self._graphs.get(key, 0)
+        if not self.use_graphs or state == 0:
+            device_stage()                                   # first poll of a bucket: plans, attributes, buffers
+            self._graphs[key] = 1
+        else:
+            if state == 1:
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    device_stage()
+                state = self._graphs[key] = g
+                if len(self._graphs) > 64:                   # stale arena generations / thresholds
+                    self._graphs = {k: v for k, v in self._graphs.items() if k[3] == self._arena.generation}
+            state.replay()
         torch.cuda.current_stream().synchronize()
         hv = host.numpy()
         res.sig_len = hv[:o0].view(np.int32)[:n_real].copy()

@@ -45,17 +45,20 @@ class PinnedArena:
         self.capacity = 0
         self.host = self.dev = self.meta_host = self.meta_dev = None
         self.meta_capacity = 0
+        self.generation = 0        # bumped whenever a buffer is re-allocated (captured graphs hold the old pointers)
 
     def reserve(self, n_samples, n_reads):
         if n_samples > self.capacity:
             self.capacity = int(n_samples * 1.25) + 4096
             self.host = torch.empty(self.capacity, dtype=torch.int16).pin_memory()
             self.dev = torch.empty(self.capacity, dtype=torch.int16, device=self.device)
+            self.generation += 1
         if n_reads > self.meta_capacity:
             self.meta_capacity = int(n_reads * 1.25) + 64
-            # int64 words: off [B+1] then n (int32 pairs packed) [B]
-            self.meta_host = torch.empty(2 * self.meta_capacity + 2, dtype=torch.int64).pin_memory()
-            self.meta_dev = torch.empty(2 * self.meta_capacity + 2, dtype=torch.int64, device=self.device)
+            # int64 words: off [B+1], then n [B] and an optional extra int32 [B] (int32 pairs packed)
+            self.meta_host = torch.empty(2 * self.meta_capacity + 4, dtype=torch.int64).pin_memory()
+            self.meta_dev = torch.empty(2 * self.meta_capacity + 4, dtype=torch.int64, device=self.device)
+            self.generation += 1
 
 
 PACK_THREADS = int(os.environ.get("RISER_PACK_THREADS", max(1, min(4, (os.cpu_count() or 2) // 2))))
@@ -86,8 +89,9 @@ class RaggedBatch:
     - skip), so that ``sig[off[b] + i]`` is still sample i of read b for every i inside the uploaded slice
     and the kernels need not know.  ``n`` is always the full prefix length.
     ``trusted=True`` skips the per-read dtype / contiguity check (the live loop's arrays come straight from
-    ``np.frombuffer(raw_data, int16)``)."""
-    def __init__(self, signals, device, arena=None, skip=None, take=None, trusted=False):
+    ``np.frombuffer(raw_data, int16)``).  ``extra_i32`` (arena path only): an int32 [B] host array uploaded with the
+    metadata in the same copy, available as ``self.extra``."""
+    def __init__(self, signals, device, arena=None, skip=None, take=None, trusted=False, extra_i32=None):
         B = len(signals)
         if not trusted:
             signals = [np.ascontiguousarray(s, dtype=np.int16) for s in signals]
@@ -125,11 +129,16 @@ class RaggedBatch:
             self.sig.copy_(arena.host[:total], non_blocking=True)
             mh = arena.meta_host.numpy()
             mh[:B + 1] = off
-            mh[B + 1:B + 1 + (B + 1) // 2].view(np.int32)[:B] = self.n_host
-            words = B + 1 + (B + 1) // 2
+            half = (B + 1) // 2
+            mh[B + 1:B + 1 + half].view(np.int32)[:B] = self.n_host
+            words = B + 1 + half
+            if extra_i32 is not None:
+                mh[words:words + half].view(np.int32)[:B] = extra_i32
+                words += half
             arena.meta_dev[:words].copy_(arena.meta_host[:words], non_blocking=True)
             self.off = arena.meta_dev[:B + 1]
-            self.n = arena.meta_dev[B + 1:words].view(torch.int32)[:B]
+            self.n = arena.meta_dev[B + 1:B + 1 + half].view(torch.int32)[:B]
+            self.extra = None if extra_i32 is None else arena.meta_dev[B + 1 + half:B + 1 + 2 * half].view(torch.int32)[:B]
         self.h2d_bytes = total * 2 + off.nbytes + self.n_host.nbytes
 
 
