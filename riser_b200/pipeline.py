@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .preprocess import RaggedBatch, PinnedArena
+from .preprocess import RaggedBatch, PinnedArena, _hostpack
 from .model import decide, DEFAULT_CHUNK
 
 _EMPTY = np.zeros(0, dtype=np.int16)
@@ -140,7 +140,9 @@ class BatchedClassifier:
         # window is known on the host (control.py:36-56, same integers as select_window_kernel): the max_len samples
         # after the end -- or nothing, while fewer than min_len samples follow it.  Reads without a cached end go up
         # whole (detection scans the whole prefix).
-        n_all = np.fromiter((len(s) for s in signals), dtype=np.int64, count=B)
+        n_all = np.zeros(B, dtype=np.int64)
+        _hostpack().lengths(signals, n_all)
+        n_all >>= 1
         has = cached >= 0
         skip = np.where(has, cached.astype(np.int64) + 1, 0)
         avail = n_all - skip
@@ -193,11 +195,17 @@ class BatchedClassifier:
         res.h2d_bytes = batch.h2d_bytes + cached.nbytes
         res.d2h_bytes = host.numel()
         # cache bookkeeping in read order (preprocess.py:93-98, control.py:96-97)
-        for r in range(B):
-            if cached[r] < 0 and det[r] > 0:
+        new = np.flatnonzero((cached < 0) & (det > 0))
+        if len(polyA_cache) + len(new) < 1000:
+            # the cache cannot reach 1000 entries during this batch: no wipe, order does not matter
+            for r in new:
                 polyA_cache[read_ids[r]] = int(det[r])
-            if res.decisions[r] != SKIPPED and len(polyA_cache) >= 1000:
-                polyA_cache.clear()
+        else:
+            for r in range(B):
+                if cached[r] < 0 and det[r] > 0:
+                    polyA_cache[read_ids[r]] = int(det[r])
+                if res.decisions[r] != SKIPPED and len(polyA_cache) >= 1000:
+                    polyA_cache.clear()
         return res
 
 
