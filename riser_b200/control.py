@@ -11,7 +11,10 @@ from .pipeline import BatchedClassifier, DECISION_NAMES, SKIPPED, ACCEPT, REJECT
 
 
 class SequencerControl():
-    def __init__(self, client, models, processor, logger, out_file):
+    def __init__(self, client, models, processor, logger, out_file, warm_up_batches=()):
+        """Same arguments as riser/control.py:5.  ``warm_up_batches`` (additive, optional): batch sizes whose launch
+        plans and CUDA graphs are built at the start of ``target`` instead of during the first polls that see them
+        (e.g. ``(512,)`` for a MinION)."""
         self.client = client
         self.models = models
         self.proc = processor
@@ -20,11 +23,15 @@ class SequencerControl():
         self.classifier = BatchedClassifier(models, processor)
         self.batch_latencies = []      # seconds from "batch in hand" to "decisions on host"
         self.batch_sizes = []
+        self.warm_up_batches = tuple(warm_up_batches)
 
     def target(self, mode, duration_h, threshold, unblock_duration=0.1):
         self.client.send_warning(
             'The sequencing run is being controlled by RISER, reads that are '
             'not in the target class will be ejected from the pore.')
+
+        if self.warm_up_batches:
+            self.classifier.warm_up(self.warm_up_batches, threshold, mode)
 
         with open(f'{self.out_filename}.csv', 'a') as out_file:
             self._write_header(out_file)

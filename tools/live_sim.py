@@ -31,7 +31,7 @@ reads = synth.raw_reads(7, min(2 * C, 2048), min_body=14000, max_body=20000, fra
 print(f"generated {len(reads)} reads in {time.time() - t0:.1f}s", file=sys.stderr)
 client = sim.LiveSimClient(reads, C, chunk=hz, n_polls=polls, first_len=hz)
 out = tempfile.mkdtemp() + "/live"
-control = SequencerControl(client, models, proc, log, out)
+control = SequencerControl(client, models, proc, log, out, warm_up_batches=(C,))
 control.start()
 control.target("deplete", 1, 0.9)
 control.finish()
