@@ -151,3 +151,31 @@ def test_offline_evaluator_matches_reference_ladder(golden_dir):
         f = ln.split("\t")
         e = opp.polya_end(sig)
         assert f[5] == str(e)
+
+
+def test_live_graph_replay_equals_eager_launches():
+    """classify_batch replays one CUDA graph per batch-size bucket; every poll brings different reads, lengths
+    and cache hits into the same buffers.  Same results, bit for bit, as the eager launch sequence; warm_up
+    builds the bucket's plan and graph without touching the caller's cache."""
+    proc = SignalProcessor(Kit.create_from_version("RNA002"))
+    models = models_for(["mRNA", "mtRNA"])
+    graph = BatchedClassifier(models, proc)
+    eager = BatchedClassifier(models, proc)
+    eager.use_graphs = False
+    assert graph.use_graphs
+    graph.warm_up((40,), 0.9, "deplete")
+    assert len(graph._graphs) == 1
+    reads = synth.raw_reads(31, 40, min_body=9000, max_body=15000, frac_no_polya=0.15)
+    cache_g, cache_e = {}, {}
+    for poll, n in enumerate((3000, 6500, 9500, 12500, 16000, 19000, 9100)):
+        order = np.random.default_rng(poll).permutation(len(reads))
+        sigs = [reads[i][1][:n + 37 * int(i)] for i in order]
+        ids = [reads[i][0] for i in order]
+        a = graph.classify_batch(sigs, ids, cache_g, 0.9, "deplete")
+        b = eager.classify_batch(sigs, ids, cache_e, 0.9, "deplete")
+        assert np.array_equal(a.decisions, b.decisions) and np.array_equal(a.sig_len, b.sig_len)
+        assert np.array_equal(a.polya_end, b.polya_end)
+        assert np.array_equal(a.p_on, b.p_on, equal_nan=True) and np.array_equal(a.p_off, b.p_off, equal_nan=True)
+        assert cache_g == cache_e
+    assert (a.sig_len > 0).any() and len(cache_g) > 0
+    assert len(graph._graphs) == 1 and not eager._graphs
