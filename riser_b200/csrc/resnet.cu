@@ -47,79 +47,90 @@ conv1d_cl_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_i
   }
 }
 
-// The same convolution, register-tiled: a CTA computes a tile of TYP = TY * PT output positions x CT output
-// channels of one read.  The weights of the channel tile ([K][Cin][CT], zero-padded) and the input rows the tile
-// touches are staged in shared memory once; thread (tx, ty) keeps PT positions x 4 channels of accumulators and
-// per (tap, input channel) does one 16-byte weight load, PT input loads (warp broadcasts) and 4 PT FMAs.
-// Geometry (TX = CT / 4, TY = 256 / TX) is chosen on the host; rows outside [0, len_in) are staged as zeros.
+// The same convolution, register-tiled and persistent: a CTA keeps the weights of its channel tile ([K][Cin][CT],
+// zero-padded) in shared memory for the whole launch and walks over work items (read, tile of TYP = TY * PT output
+// positions), staging for each the input rows the tile touches.  Thread (tx, ty) keeps PT positions x 4 channels of
+// accumulators and per (tap, input channel) does one 16-byte weight load, PT input loads (warp broadcasts) and
+// 4 PT FMAs.  Geometry (TX = CT / 4, TY, the block size TX * TY rounded up to a warp) is chosen on the host so
+// that the position tiles of a read waste few rows; rows outside [0, len_in) are staged as zeros and tiles beyond
+// a read's output length are skipped.
 template <int PT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)   // 85 registers: three CTAs per SM measured faster than two (121) or four (spills)
 conv1d_cl_tiled_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_in,
                        const float* __restrict__ w, const float* __restrict__ bias,
                        const float* __restrict__ residual, float* __restrict__ out,
-                       const int32_t* __restrict__ len_out, int Lin_pad, int Lout_pad, int Cin, int Cout,
-                       int K, int stride, int pad, int relu, int CT, int TX, int TY, int pitch) {
+                       const int32_t* __restrict__ len_out, int B, int Lin_pad, int Lout_pad, int Cin, int Cout,
+                       int K, int stride, int pad, int relu, int CT, int TX, int TY, int pitch, int tiles,
+                       uint32_t cin_magic) {
   extern __shared__ __align__(16) float smem_f[];
-  const int b = blockIdx.z;
   const int co0 = blockIdx.y * CT;
   const int TYP = TY * PT;
-  const int t0 = blockIdx.x * TYP;
-  const int Lo = len_out[b];
-  if (t0 >= Lo) return;                               // nothing of this tile is written
-  const int Lb = len_in[b];
   const int rows = (TYP - 1) * stride + K;
   float* w_s = smem_f;                                // [K * Cin][CT]
   float* in_s = smem_f + ((K * Cin * CT + 3) & ~3);   // [rows][pitch]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < K * Cin * CT; i += 256) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < K * Cin * CT; i += nthr) {
     const int c = i % CT, kc = i / CT;
     w_s[i] = (co0 + c < Cout) ? __ldg(w + static_cast<int64_t>(kc) * Cout + co0 + c) : 0.f;
   }
-  const int ti0 = t0 * stride - pad;
-  const float* inb = in + static_cast<int64_t>(b) * Lin_pad * Cin;
-  for (int i = tid; i < rows * Cin; i += 256) {
-    const int r = i / Cin, ci = i - r * Cin;
-    const int ti = ti0 + r;
-    in_s[r * pitch + ci] = (ti >= 0 && ti < Lb) ? __ldg(inb + static_cast<int64_t>(ti) * Cin + ci) : 0.f;
-  }
-  __syncthreads();
   const int tx = tid % TX, ty = tid / TX;
-  if (ty >= TY) return;
-  float acc[PT][4];
+  const int c0 = co0 + 4 * tx;
+  float bv[4];
 #pragma unroll
-  for (int p = 0; p < PT; ++p)
+  for (int c = 0; c < 4; ++c) bv[c] = (c0 + c < Cout) ? __ldg(bias + c0 + c) : 0.f;
+  const int n_items = B * tiles;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / tiles;
+    const int t0 = (item - b * tiles) * TYP;
+    const int Lo = len_out[b];
+    if (t0 >= Lo) continue;                           // block-uniform: nothing of this tile is written
+    const int Lb = len_in[b];
+    const int ti0 = t0 * stride - pad;
+    const float* inb = in + static_cast<int64_t>(b) * Lin_pad * Cin;
+    __syncthreads();                                  // the previous item's rows are no longer read (and w_s is complete)
+    for (int i = tid; i < rows * Cin; i += nthr) {
+      const int r = (Cin == 1) ? i : static_cast<int>(__umulhi(static_cast<uint32_t>(i), cin_magic));   // i / Cin
+      const int ci = i - r * Cin;
+      const int ti = ti0 + r;
+      in_s[r * pitch + ci] = (ti >= 0 && ti < Lb) ? __ldg(inb + static_cast<int64_t>(ti) * Cin + ci) : 0.f;
+    }
+    __syncthreads();
+    if (ty >= TY) continue;                           // lanes that round the block up to a warp
+    float acc[PT][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
-  const float* a_base = in_s + ty * PT * stride * pitch;
-  const float* w_base = w_s + 4 * tx;
-  for (int k = 0; k < K; ++k) {
-    const float* a_k = a_base + k * pitch;
-    const float* w_k = w_base + static_cast<size_t>(k) * Cin * CT;
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+    const float* a_base = in_s + ty * PT * stride * pitch;
+    const float* w_base = w_s + 4 * tx;
+    for (int k = 0; k < K; ++k) {
+      const float* a_k = a_base + k * pitch;
+      const float* w_k = w_base + static_cast<size_t>(k) * Cin * CT;
 #pragma unroll 4
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float4 wv = *reinterpret_cast<const float4*>(w_k + ci * CT);
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float4 wv = *reinterpret_cast<const float4*>(w_k + ci * CT);
 #pragma unroll
-      for (int p = 0; p < PT; ++p) {
-        const float a = a_k[p * stride * pitch + ci];
-        acc[p][0] = fmaf(a, wv.x, acc[p][0]);
-        acc[p][1] = fmaf(a, wv.y, acc[p][1]);
-        acc[p][2] = fmaf(a, wv.z, acc[p][2]);
-        acc[p][3] = fmaf(a, wv.w, acc[p][3]);
+        for (int p = 0; p < PT; ++p) {
+          const float a = a_k[p * stride * pitch + ci];
+          acc[p][0] = fmaf(a, wv.x, acc[p][0]);
+          acc[p][1] = fmaf(a, wv.y, acc[p][1]);
+          acc[p][2] = fmaf(a, wv.z, acc[p][2]);
+          acc[p][3] = fmaf(a, wv.w, acc[p][3]);
+        }
       }
     }
-  }
-  const int c0 = co0 + 4 * tx;
 #pragma unroll
-  for (int p = 0; p < PT; ++p) {
-    const int t = t0 + ty * PT + p;
-    if (t >= Lo) break;
-    const int64_t o = (static_cast<int64_t>(b) * Lout_pad + t) * Cout + c0;
+    for (int p = 0; p < PT; ++p) {
+      const int t = t0 + ty * PT + p;
+      if (t >= Lo) break;
+      const int64_t o = (static_cast<int64_t>(b) * Lout_pad + t) * Cout + c0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c0 + c >= Cout) break;
-      float v = acc[p][c] + __ldg(bias + c0 + c);
-      if (residual) v += residual[o + c];
-      out[o + c] = relu ? fmaxf(v, 0.f) : v;
+      for (int c = 0; c < 4; ++c) {
+        if (c0 + c >= Cout) break;
+        float v = acc[p][c] + bv[c];
+        if (residual) v += residual[o + c];
+        out[o + c] = relu ? fmaxf(v, 0.f) : v;
+      }
     }
   }
 }
@@ -217,17 +228,22 @@ extern "C" int riser_conv1d_cl(const float* in, const int32_t* len_in, const flo
   RISER_REQUIRE(in && len_in && w && bias && out && len_out, "riser_conv1d_cl: null pointer");
   RISER_REQUIRE(B > 0 && Lin_pad > 0 && Lout_pad > 0 && Cin > 0 && Cout > 0 && K > 0 && stride > 0 && pad >= 0,
                 "riser_conv1d_cl: bad shape");
-  // register-tiled kernel whenever its weight tile and input rows fit shared memory (every ResNet shape does)
+  // register-tiled persistent kernel whenever its weight tile and input rows fit shared memory (every ResNet shape does)
   {
     constexpr int PT = 8;
     // channel tile: all output channels when <= 128 (a 67-channel layer must not pay for a second, almost empty tile)
     const int c4 = (Cout + 3) & ~3;
     const int CT = c4 <= 128 ? c4 : 64;
-    const int TX = CT / 4, TY = 256 / TX, TYP = TY * PT;
+    const int TX = CT / 4, ty_max = 256 / TX;
+    // position tiles of a read: as few as the block allows, then the smallest TY that still covers the read with them
+    const int tiles = (Lout_pad + ty_max * PT - 1) / (ty_max * PT);
+    const int TY = std::min(ty_max, ((Lout_pad + tiles - 1) / tiles + PT - 1) / PT);
+    const int TYP = TY * PT;
+    const int threads = std::min(256, (TX * TY + 31) & ~31);
     const int pitch = Cin | 1;                                    // odd row pitch: the ty's of a warp hit distinct banks
     const int rows = (TYP - 1) * stride + K;
     const size_t smem = (static_cast<size_t>((K * Cin * CT + 3) & ~3) + static_cast<size_t>(rows) * pitch) * sizeof(float);
-    if (smem <= 200 * 1024 && B <= 65535 && !getenv("RISER_RESNET_NAIVE")) {
+    if (smem <= 200 * 1024 && !getenv("RISER_RESNET_NAIVE")) {
       static size_t configured[64] = {0};
       int dev = 0;
       RISER_CUDA_TRY(cudaGetDevice(&dev));
@@ -236,10 +252,16 @@ extern "C" int riser_conv1d_cl(const float* in, const int32_t* len_in, const flo
                                             static_cast<int>(smem)));
         configured[dev & 63] = smem;
       }
-      const dim3 grid((Lout_pad + TYP - 1) / TYP, (Cout + CT - 1) / CT, B);
-      conv1d_cl_tiled_kernel<PT><<<grid, 256, smem, as_stream(stream)>>>(in, len_in, w, bias, residual, out, len_out,
-                                                                         Lin_pad, Lout_pad, Cin, Cout, K, stride, pad,
-                                                                         relu, CT, TX, TY, pitch);
+      int per_sm = 0;
+      RISER_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv1d_cl_tiled_kernel<PT>, threads, smem));
+      const int64_t n_items = static_cast<int64_t>(B) * tiles;
+      const int n_ct = (Cout + CT - 1) / CT;
+      const int gx = static_cast<int>(std::min<int64_t>(n_items, std::max(1, 148 * std::max(per_sm, 1) / n_ct)));
+      const uint32_t cin_magic = static_cast<uint32_t>((0x100000000ull + Cin - 1) / Cin);
+      RISER_REQUIRE(static_cast<int64_t>(rows) * Cin < (1 << 24), "riser_conv1d_cl: tile too large");
+      conv1d_cl_tiled_kernel<PT><<<dim3(gx, n_ct), threads, smem, as_stream(stream)>>>(
+          in, len_in, w, bias, residual, out, len_out, B, Lin_pad, Lout_pad, Cin, Cout, K, stride, pad, relu, CT, TX, TY,
+          pitch, tiles, cin_magic);
       RISER_CUDA_TRY(cudaGetLastError());
       return RISER_OK;
     }
