@@ -278,10 +278,14 @@ def main():
     # the bracket covers layer 0 (CUDA cores) + conv layers 1..11; take layer 0's launches out
     conv_ms -= mdl.time_layer0(clf._buffers(B)["x"], length, L)
     # ---- the HBM-bound stage: riser_normalise alone (6 bytes per sample: int16 in, fp32 out), L2 flushed
+    # (a kernel timed alone: the board is first given half a second to leave the power-capped clock the timed
+    #  steps drove it into -- the HBM peak it is compared with was measured the same way)
     L_ = _lib.lib()
     xbuf = clf._buffers(B)["x"]
+    torch.cuda.synchronize()
+    time.sleep(0.5)
     nev = []
-    for _ in range(5):
+    for _ in range(7):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -290,7 +294,7 @@ def main():
         b.record()
         nev.append((a, b))
     torch.cuda.synchronize()
-    norm_ms = sorted(a.elapsed_time(b) for a, b in nev)[len(nev) // 2]
+    norm_ms = sorted(a.elapsed_time(b) for a, b in nev[2:])[(len(nev) - 2) // 2]      # first two launches: warm-up
     # ---- e2e: the public streaming API with HOST buffers.  Every step copies its 131 MB of
     #      pinned int16 input H2D and brings decisions + probabilities back D2H; the copy of
     #      step k+1 overlaps the kernels of step k (FixedBatchPipeline, two slots).
