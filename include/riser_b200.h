@@ -86,7 +86,8 @@ int riser_normalise_max_len(void);
  * riser/model.py:25 applies) into out[b * ld_out + i], i < len[b].  Elements
  * i >= len[b] of the row are not written.  len[b] == 0 writes nothing.
  * mad == 0 writes zeros (preprocess.py:122-124).
- * out must be 16-byte aligned and ld_out a multiple of 4.
+ * out must be 16-byte aligned and ld_out a multiple of 4.  max_len bounds every len[b]
+ * (<= riser_normalise_max_len()); a longer window is processed as its first max_len samples.
  * The window is staged by a bulk copy of whole 16-byte blocks: the sig allocation must
  * reach the end of the 16-byte block that holds a window's last sample (any cudaMalloc'd
  * buffer does).  off[b] may be a VIRTUAL start (the caller uploaded only part of read b),

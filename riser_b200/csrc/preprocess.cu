@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 5)
 normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
                  const int32_t* __restrict__ start, const int32_t* __restrict__ len, int B,
                  float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ med2_mad4,
-                 int nbuf, int buf_samples, int dbg) {
+                 int nbuf, int buf_samples, int max_len, int dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SelectScratch& s = *reinterpret_cast<SelectScratch*>(smem_raw);
   int16_t* stage_base = reinterpret_cast<int16_t*>(smem_raw + ((sizeof(SelectScratch) + 127) & ~size_t(127)));
@@ -242,7 +242,7 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     nr = 0;
     gr = sig;
     if (r < B) {
-      nr = len[r];
+      nr = min(len[r], max_len);      // memory safety: a window longer than the caller's max_len is cut to it
       gr = sig + off[r] + (start ? start[r] : 0);
     }
   };
@@ -881,7 +881,7 @@ extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int
   if (ctas_env > 0) per_sm = std::min(per_sm, ctas_env);
   const int grid = std::min(B, sm_count() * per_sm);
   normalise_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, start, len, B, out, ld_out,
-                                                               med2_mad4, nbuf, buf_samples, dbg);
+                                                               med2_mad4, nbuf, buf_samples, max_len, dbg);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

@@ -237,3 +237,19 @@ def test_normalise_kernel_variants(env):
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_normalise_cuts_windows_at_max_len():
+    """A len[b] above the max_len the caller states must not run past the staging buffer: the window is processed
+    as its first max_len samples (include/riser_b200.h)."""
+    from riser_b200 import RaggedBatch, _lib
+    rng = np.random.default_rng(9)
+    sigs = [synth.body(rng, 9000), synth.body(rng, 5000)]
+    batch = RaggedBatch(sigs, torch.device("cuda"))
+    max_len = 6000
+    out = torch.full((2, max_len), 7.0, device="cuda")
+    _lib.check(_lib.lib().riser_normalise(_lib.ptr(batch.sig), _lib.ptr(batch.off), None, _lib.ptr(batch.n), 2, max_len,
+                                          _lib.ptr(out), out.stride(0), None, _lib.stream_ptr()), "riser_normalise")
+    out = out.cpu().numpy()
+    assert np.array_equal(out[0], oracle32(sigs[0][:max_len]))
+    assert np.array_equal(out[1, :5000], oracle32(sigs[1])) and np.all(out[1, 5000:] == 7.0)
