@@ -3,7 +3,13 @@ CPU only -- compared with the plain numpy slice assignments it replaces."""
 import numpy as np
 import pytest
 
+from riser_b200 import build
 from riser_b200.preprocess import _hostpack
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build.build_hostpack()
 
 
 def _reads(rng, B):
