@@ -112,7 +112,8 @@ int riser_normalise_f32(const float* sig, const int64_t* off, const int32_t* len
  * polya_start (optional, may be NULL): the poly(A) start window the scan found, -1 for
  * None (riser/test.py:80-117 get_polyA_coords returns both, at resolution 500 / MAD 20).
  * stats (optional, may be NULL): int32 [B, max_windows, 3] = {sum, 2*median,
- * 4*MAD} per 500-sample window.                                                */
+ * 4*MAD} per 500-sample window.  At most the first 512 windows (256,000 samples) of a
+ * prefix are scanned; the live loop never holds more than ~18,500 (control.py:42-46).    */
 int riser_polya_end(const int16_t* sig, const int64_t* off, const int32_t* n, int B,
                     int32_t* polya_end, int32_t* polya_start, int32_t* stats, int max_windows,
                     riser_stream_t stream);
