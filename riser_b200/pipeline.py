@@ -37,6 +37,20 @@ def bucket_size(n):
         b *= 2
 
 
+def upload_ranges(n, cached_end, min_len, max_len):
+    """Which samples of each read the device will look at (int64 skip / take per read).  A read whose poly(A) end
+    is cached needs no detection and its window is signal[end + 1 : end + 1 + max_len] when at least min_len
+    samples follow the end, nothing otherwise (control.py:36-60 / preprocess.py:87-102 -- the integers
+    select_window_kernel computes); a read without a cached end is needed whole (detection, or the fixed trim)."""
+    n = np.asarray(n, dtype=np.int64)
+    cached_end = np.asarray(cached_end)
+    has = cached_end >= 0
+    skip = np.where(has, cached_end.astype(np.int64) + 1, 0)
+    avail = n - skip
+    take = np.where(has, np.where(avail >= min_len, np.minimum(avail, max_len), 0), n)
+    return skip, take
+
+
 class BatchResult:
     """Host-side result of one batch: ``decisions`` uint8 [B], ``p_on`` / ``p_off``
     float32 [B, M], ``sig_len`` int32 [B] (post-trim window length, 0 = skipped),
@@ -143,10 +157,7 @@ class BatchedClassifier:
         n_all = np.zeros(B, dtype=np.int64)
         _hostpack().lengths(signals, n_all)
         n_all >>= 1
-        has = cached >= 0
-        skip = np.where(has, cached.astype(np.int64) + 1, 0)
-        avail = n_all - skip
-        take = np.where(has, np.where(avail >= self.min_len, np.minimum(avail, self.max_len), 0), n_all)
+        skip, take = upload_ranges(n_all, cached, self.min_len, self.max_len)
         batch = RaggedBatch(signals, self.device, arena=self._arena, skip=skip, take=take, trusted=True,
                             extra_i32=cached)
         # packed pinned result buffer: len | detected | probs | decisions (4-byte fields first)
