@@ -26,6 +26,10 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm (rank 0 alone does the work) is to use all host threads
+if "reference" in sys.argv and os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import numpy as np
 import torch
 
