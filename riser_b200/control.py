@@ -1,102 +1,69 @@
-"""Batched drop-in for riser/control.py's SequencerControl.
+"""The ReadUntil loop with a batched body: a drop-in for ``SequencerControl`` of riser/control.py.
 
-Same constructor, same ``start`` / ``target`` / ``finish`` methods, same CSV rows,
-counters, cache reset and ReadUntil calls (riser/control.py:4-153); only the serial
-per-read body of the loop (control.py:31-93) is replaced by ONE call to
-``BatchedClassifier.classify_batch`` per ``client.get_read_batch()``.
+What the sequencer, the log and the CSV see is what riser/control.py:4-153 produces -- the take-over and
+stop warnings, one CSV row per assessed read in read order, ``unblock`` for rejects, ``stop_receiving`` for
+every read that needs no further look, the per-minute tally, the poly(A)-cache wipe at 1000 entries.  How a
+poll is worked through is different: the reference walks the reads of a poll one by one through trim ->
+gate -> normalise -> classify -> decide (control.py:31-93); here the whole poll goes to
+``BatchedClassifier.classify_batch`` once, the decision codes come back as one array, and the rows and the
+three read lists are cut out of that array.
 """
 import time
 
+import numpy as np
+
 from .pipeline import BatchedClassifier, DECISION_NAMES, SKIPPED, ACCEPT, REJECT, NO_DECISION
+
+CSV_HEADER = 'batch_start,read_id,channel,sig_length,models,prob_targets,threshold,mode,decision\n'   # control.py:146
+TAKE_OVER_NOTICE = ('The sequencing run is being controlled by RISER, reads that are '
+                    'not in the target class will be ejected from the pore.')                         # control.py:13-14
+PROGRESS_PERIOD_S = 60                                                                                # control.py:19,116
+
+
+class _MinuteTally:
+    """assessed / accepted / rejected since the last progress line (control.py:21-23,108-117)."""
+    def __init__(self, logger, now):
+        self.logger = logger
+        self.due = now + PROGRESS_PERIOD_S
+        self.assessed = self.accepted = self.rejected = 0
+
+    def add(self, assessed, accepted, rejected):
+        self.assessed += assessed
+        self.accepted += accepted
+        self.rejected += rejected
+
+    def maybe_report(self, batch_start):
+        if batch_start <= self.due:
+            return
+        self.logger.info(f"In the last minute {self.assessed} signals "
+                         f"were assessed, {self.accepted} were "
+                         f"accepted and {self.rejected} were rejected")
+        self.assessed = self.accepted = self.rejected = 0
+        self.due = batch_start + PROGRESS_PERIOD_S
+
+
+def _sequencer_key(read):
+    """What unblock / stop_receiving want for a read: its number with minknow-api <= v5, its id from v6 on
+    (control.py:137-143)."""
+    return read.number if hasattr(read, "number") else read.id
 
 
 class SequencerControl():
     def __init__(self, client, models, processor, logger, out_file, warm_up_batches=()):
-        """Same arguments as riser/control.py:5.  ``warm_up_batches`` (additive, optional): batch sizes whose launch
-        plans and CUDA graphs are built at the start of ``target`` instead of during the first polls that see them
-        (e.g. ``(512,)`` for a MinION)."""
+        """Arguments as riser/control.py:5.  ``warm_up_batches`` (additive, optional): batch sizes whose launch
+        plans and CUDA graphs are built at the start of ``target`` instead of during the first polls that see
+        them (e.g. ``(512,)`` for a MinION)."""
         self.client = client
         self.models = models
         self.proc = processor
         self.logger = logger
         self.out_filename = out_file
         self.classifier = BatchedClassifier(models, processor)
+        self.warm_up_batches = tuple(warm_up_batches)
         self.batch_latencies = []      # seconds from "batch in hand" to "decisions on host"
         self.batch_sizes = []
-        self.warm_up_batches = tuple(warm_up_batches)
 
-    def target(self, mode, duration_h, threshold, unblock_duration=0.1):
-        self.client.send_warning(
-            'The sequencing run is being controlled by RISER, reads that are '
-            'not in the target class will be ejected from the pore.')
-
-        if self.warm_up_batches:
-            self.classifier.warm_up(self.warm_up_batches, threshold, mode)
-
-        with open(f'{self.out_filename}.csv', 'a') as out_file:
-            self._write_header(out_file)
-            run_start = time.monotonic()
-            progress_time = run_start + 60
-            duration_s = self._hours_to_seconds(duration_h)
-            n_assessed = 0
-            n_rejected = 0
-            n_accepted = 0
-            polyA_cache = {}
-            while self.client.is_running() and time.monotonic() < run_start + duration_s:
-                # Get batch of reads to process
-                batch_start = time.monotonic()
-                reads_to_reject = []
-                reads_to_accept = []
-                reads_unclassified = []
-                batch = list(self.client.get_read_batch())
-                signals = [self.client.get_raw_signal(read) for _, read in batch]
-                t0 = time.monotonic()
-                res = self.classifier.classify_batch(signals, [read.id for _, read in batch],
-                                                     polyA_cache, threshold, mode)
-                self.batch_latencies.append(time.monotonic() - t0)
-                self.batch_sizes.append(len(batch))
-
-                for i, (channel, read) in enumerate(batch):
-                    code = int(res.decisions[i])
-                    if code == SKIPPED:          # the `continue` branches, control.py:50,56
-                        continue
-                    n_assessed += 1
-                    if code == ACCEPT:
-                        reads_to_accept.append((channel, self._get_read_id(read)))
-                    elif code == REJECT:
-                        reads_to_reject.append((channel, self._get_read_id(read)))
-                    elif code == NO_DECISION:
-                        reads_unclassified.append((channel, self._get_read_id(read)))
-                    self._write(out_file, batch_start, channel, read.id, int(res.sig_len[i]),
-                                self.models, res.p_on[i], threshold, mode, DECISION_NAMES[code])
-
-                # Send reject requests
-                self.client.reject_reads(reads_to_reject, unblock_duration)
-                n_rejected += len(reads_to_reject)
-
-                # Don't need to reassess the reads that were rejected, accepted
-                # or couldn't be classified after the maximum input length
-                done = reads_to_reject + reads_to_accept + reads_unclassified
-                self.client.finish_processing_reads(done)
-                n_accepted += len(reads_to_accept)
-
-                # Log progress each minute
-                if batch_start > progress_time:
-                    self.logger.info(f"In the last minute {n_assessed} signals "
-                                     f"were assessed, {n_accepted} were "
-                                     f"accepted and {n_rejected} were rejected")
-                    n_assessed = 0
-                    n_rejected = 0
-                    n_accepted = 0
-                    progress_time = batch_start + 60
-            else:
-                self.client.send_warning('RISER has stopped running.')
-                if not self.client.is_running():
-                    self.logger.info('Client has stopped.')
-                if time.monotonic() > run_start + duration_s:
-                    self.logger.info(f'RISER has timed out after {duration_h} '
-                                     'hours as requested.')
-
+    # ------------------------------------------------------------------ riser.py's three calls
     def start(self):
         self.client.start_streaming_reads()
         self.logger.info('Live read stream started.')
@@ -105,23 +72,50 @@ class SequencerControl():
         self.client.reset()
         self.logger.info('Client reset and live read stream ended.')
 
-    def _hours_to_seconds(self, hours):
-        return hours * 60 * 60
+    def target(self, mode, duration_h, threshold, unblock_duration=0.1):
+        self.client.send_warning(TAKE_OVER_NOTICE)
+        if self.warm_up_batches:
+            self.classifier.warm_up(self.warm_up_batches, threshold, mode)
+        model_names = ";".join(m.target for m in self.models)
+        polyA_cache = {}       # one dict for the run; classify_batch stores found ends and wipes it at 1000 entries
+        with open(f'{self.out_filename}.csv', 'a') as sink:
+            sink.write(CSV_HEADER)
+            began = time.monotonic()
+            deadline = began + duration_h * 3600
+            tally = _MinuteTally(self.logger, began)
+            while self.client.is_running() and time.monotonic() < deadline:
+                self._poll(sink, tally, polyA_cache, model_names, mode, threshold, unblock_duration)
+            self.client.send_warning('RISER has stopped running.')
+            if not self.client.is_running():
+                self.logger.info('Client has stopped.')
+            if time.monotonic() > deadline:
+                self.logger.info(f'RISER has timed out after {duration_h} '
+                                 'hours as requested.')
 
-    def _get_read_id(self, read):
-        # Support for minknow-api <= v5.*
-        if hasattr(read, "number"):
-            return read.number
-        # Support for minknow-api >= v6.*
-        else:
-            return read.id
+    # ------------------------------------------------------------------ one poll
+    def _poll(self, sink, tally, polyA_cache, model_names, mode, threshold, unblock_duration):
+        batch_start = time.monotonic()
+        batch = list(self.client.get_read_batch())
+        signals = [self.client.get_raw_signal(read) for _, read in batch]
+        t0 = time.monotonic()
+        res = self.classifier.classify_batch(signals, [read.id for _, read in batch], polyA_cache, threshold, mode)
+        self.batch_latencies.append(time.monotonic() - t0)
+        self.batch_sizes.append(len(batch))
 
-    def _write_header(self, csv_file):
-        csv_file.write('batch_start,read_id,channel,sig_length,models,prob_targets,threshold,mode,decision\n')
+        codes = np.asarray(res.decisions)
+        assessed = np.flatnonzero(codes != SKIPPED)          # the others hit a `continue` (control.py:50,56)
+        stamp = f'{batch_start:.0f}'
+        sink.writelines(
+            f'{stamp},{batch[i][1].id},{batch[i][0]},{int(res.sig_len[i])},{model_names},'
+            f'{";".join(str(float(p)) for p in res.p_on[i])},{threshold},{mode},{DECISION_NAMES[int(codes[i])]}\n'
+            for i in assessed)
 
-    def _write(self, csv_file, batch_start, channel, read, sig_length,
-               models, p_on_targets, threshold, mode, decision):
-        csv_file.write(f'{batch_start:.0f},{read},{channel},{sig_length},'
-                       f'{";".join([m.target for m in models])},'
-                       f'{";".join([str(float(p)) for p in p_on_targets])},'
-                       f'{threshold},{mode},{decision}\n')
+        def keyed(code):
+            return [(batch[i][0], _sequencer_key(batch[i][1])) for i in np.flatnonzero(codes == code)]
+
+        rejects, accepts, undecided = keyed(REJECT), keyed(ACCEPT), keyed(NO_DECISION)
+        self.client.reject_reads(rejects, unblock_duration)
+        # rejected, accepted and exhausted (max length, still undecided) reads need no further look
+        self.client.finish_processing_reads(rejects + accepts + undecided)
+        tally.add(len(assessed), len(accepts), len(rejects))
+        tally.maybe_report(batch_start)
