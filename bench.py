@@ -13,9 +13,16 @@ synthetic already-trimmed squiggle chunks: BASELINE.json configs[1], RNA004 mode
            batch and D2H of decisions + probabilities inside the timed region
   roofline the tcgen05 conv stack (layers 1..11): algorithmic FLOPs / CUDA-event time of that
            stage, against the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the oracle port of the reference's CPU path
-           (numpy normalise + torch-CPU ConvNet per read, riser/control.py:63-71) on the
-           box's host cores, on a bounded sample of the same workload.
+  cpu_baseline / --impl reference: the reference's OWN CPU path -- SignalProcessor.mad_normalise
+           (np.vectorize, riser/preprocess.py:108-147) + Model.classify (riser/model.py:22-28) per read as
+           riser/control.py:63-71 -- imported from oracle/_ref (the byte-compiled reference, see
+           oracle/build_ref.py; `kind: "reference"`), on the box's host cores, on a bounded sample of the
+           same workload.  The oracle port (vectorised numpy normalise) and a 1-thread run are reported beside it.
+  torch_cuda_baseline: "PyTorch on B200" -- the reference's Model.classify on cuda at batch 1 (how RISER runs)
+           and its ConvNet on the whole batch through cuDNN (TF32, and bf16 autocast), same box, same inputs.
+  latency  p50 / p99 per poll of the live loop (BASELINE config 5): 512 channels x 2 models, 3000 x 1.
+
+    python bench.py --reads 1000000 [--gpus N]      BASELINE config 4: R reads of 12,048 samples sharded r mod G
 """
 import argparse
 import json
@@ -61,6 +68,18 @@ def workload_name(batch, length):
             f"{length} int16 samples per chunk (4 s @ 4 kHz), already trimmed")
 
 
+def shared_config(batch, length):
+    """The `config` object: IDENTICAL in both arms (ours / --impl reference) -- what differs between the arms
+    (precision mode, sample sizes, launch counts) lives in other keys of the line."""
+    return {"workload": workload_name(batch, length), "batch_per_gpu": batch, "samples_per_chunk": length,
+            "network": "ConvNet 12 x [Conv1d k3 + ReLU + MaxPool(2,2)] -> GAP -> Linear(1702, 2) "
+                       "(riser/nets/cnn.py, the net riser/model.py:18 builds; BASELINE's metric says ResNet, "
+                       "which nothing on the riser.py path instantiates -- SURVEY 0.1)",
+            "step": "median/MAD normalise + outlier smoothing -> network -> softmax -> accept/reject decision",
+            "flops_per_read": flops_per_read(length),
+            "cache": "GPU arm: L2 flushed between timed steps (256 MiB write), inputs 393 MB > L2; CPU arm: n/a"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -68,6 +87,32 @@ def peaks():
             p = json.load(f)
         return p.get("bf16_tflops_sustained", p.get("bf16_tflops")), p.get("hbm_gbs"), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def burst_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("bf16_tflops", 1590.0)
+    return 1590.0
+
+
+def pass_equivalents(length, precision, f8_from):
+    """fp16-pass-equivalents of tensor work executed per algorithmic FLOP of the conv stack (FLOP-weighted over
+    layers 1..11): F16 1, F16_W2 2, F16_X3 3; F16_F8: 3 in layers < f8_from (hi + lo planes), 2 from there on
+    (fp16 pass + one e4m3 pass of twice the K at twice the rate).  1 / this = the structural ceiling of
+    roofline.frac at a perfect tensor pipe."""
+    if precision != 3:
+        return {0: 1.0, 1: 2.0, 2: 3.0}[precision]
+    tot = w = 0.0
+    cin, l = 1, int(length)
+    for i, c in enumerate(CHANNELS):
+        f = 2 * 3 * cin * c * l
+        if i >= 1:
+            tot += f
+            w += f * (2.0 if i >= f8_from else 3.0)
+        cin, l = c, l // 2
+    return w / tot
 
 
 class ClockSampler(threading.Thread):
@@ -143,45 +188,274 @@ def cpu_reads(sample_reads, length, seed=4321):
     return [pool[i % len(pool)] for i in range(sample_reads)]
 
 
-def time_cpu_path(X, state, threads):
-    """The oracle port of riser/control.py:63-71 per read, on `threads` host threads."""
-    from oracle import preprocess_oracle as pp
-    from oracle import convnet_oracle as net
+class CpuPath:
+    """The reference's CPU implementation of one read of the path, riser/control.py:63-71:
+    ``signal = proc.mad_normalise(signal); p_off, p_on = model.classify(signal)``.
+
+    kind "reference": the reference's own SignalProcessor / Model (imported from /root/reference in the build
+    container, from the byte-compiled oracle/_ref on the GPU box), Model forced onto the CPU, weights loaded through
+    its own torch.load path.  kind "port": the oracle restatement (vectorised numpy normalise -- faster than the
+    reference's np.vectorize loop -- + torch-CPU ConvNet)."""
+    def __init__(self, kind=None):
+        from riser_b200 import synth
+        from oracle import refshim
+        self.kind = kind or ("reference" if refshim.available() else "port")
+        if self.kind == "reference":
+            import tempfile
+            ref = refshim.load()
+            ref.model.Model._get_device = lambda self_: torch.device("cpu")      # riser/model.py:30-32
+            self.source = refshim.kind()
+            with tempfile.TemporaryDirectory() as tmp:
+                path = synth.save_state_dict(0, os.path.join(tmp, "mRNA_model_RNA004.pth"))
+                self.model = ref.model.Model(path, refshim.cnn_config(), logging.getLogger("reference"), "mRNA")
+            self.proc = ref.preprocess.SignalProcessor(ref.preprocess.Kit.create_from_version("RNA004"))
+            self.read = lambda x: self.model.classify(self.proc.mad_normalise(x))
+        else:
+            from oracle import preprocess_oracle as pp
+            from oracle import convnet_oracle as net
+            self.source = "oracle port"
+            state = synth.state_dict(0)
+            self.read = lambda x: net.classify(state, pp.mad_normalise(x))
+
+    def rate(self, X, threads):
+        torch.set_num_threads(threads)
+        for r in range(min(2, len(X))):
+            self.read(X[r])
+        t0 = time.perf_counter()
+        for r in range(len(X)):
+            self.read(X[r])
+        return len(X) / (time.perf_counter() - t0)
+
+
+def host_threads():
+    cores = os.cpu_count() or 1
+    return min(cores, torch.get_num_threads() if torch.get_num_threads() > 1 else cores)
+
+
+def cpu_baseline(length, n_ref, n_port, n_one):
+    """cpu_baseline object of our arm's line: the reference on all host threads (bounded sample), with the port
+    and a 1-thread run of the reference beside it."""
+    threads = host_threads()
+    path = CpuPath()
+    out = {"value": path.rate(cpu_reads(n_ref, length), threads), "unit": UNIT, "cores": threads,
+           "kind": path.kind, "source": path.source,
+           "sample": f"{n_ref} reads of {length} samples, per-read loop (mad_normalise + Model.classify, "
+                     f"riser/control.py:63-71), torch threads = {threads}"}
+    if n_one:
+        out["one_thread"] = {"value": path.rate(cpu_reads(n_one, length), 1), "cores": 1, "sample": f"{n_one} reads"}
+    if n_port and path.kind != "port":
+        port = CpuPath("port")
+        out["port"] = {"value": port.rate(cpu_reads(n_port, length), threads), "cores": threads,
+                       "sample": f"{n_port} reads", "note": "oracle restatement, vectorised numpy normalise"}
     torch.set_num_threads(threads)
-    for r in range(min(2, len(X))):
-        net.classify(state, pp.mad_normalise(X[r]))
-    t0 = time.perf_counter()
-    for r in range(len(X)):
-        net.classify(state, pp.mad_normalise(X[r]))
-    return len(X) / (time.perf_counter() - t0)
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU path on the host cores (rank 0 alone; all host threads)."""
     if rank != 0:
         return
-    from riser_b200 import synth
-    cores = os.cpu_count() or 1
-    threads = min(cores, torch.get_num_threads() if torch.get_num_threads() > 1 else cores)
-    state = synth.state_dict(0)
+    threads = host_threads()
+    path = CpuPath()
     per_step = args.ref_reads
     X = cpu_reads(per_step, args.length)
     for _ in range(args.warmup):
-        time_cpu_path(X[:2], state, threads)
+        path.rate(X[:2], threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        time_cpu_path(X, state, threads)
+        path.rate(X, threads)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} reads of {args.length} samples per step, per-read loop (normalise + classify), oracle port"
+    sample = (f"{per_step} reads of {args.length} samples per step, per-read loop (mad_normalise + Model.classify, "
+              f"riser/control.py:63-71), {path.source}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch, args.length), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic",
+            "config": shared_config(args.batch, args.length),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": path.kind, "source": path.source,
+                             "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
+
+
+def torch_cuda_baseline(host_i16, dev, B, L, iters=3):
+    """"PyTorch on B200" (SURVEY 2.3 / 8d): the reference's own modules on this GPU.
+      batch1  : Model.classify per read on cuda (riser/model.py:22-28 -- how RISER runs), normalised input
+                resident on the host as float64 like control.py hands it over
+      batched : ConvNet(X[B, L]) through cuDNN on the whole batch, TF32 convs (torch's default:
+                cudnn.allow_tf32) and bf16 autocast; network only (no normalise, no decision)
+    Reads/s; None + a reason when the reference cannot be imported."""
+    from oracle import refshim
+    from riser_b200 import synth
+    if not refshim.available():
+        return {"unavailable": "reference not importable (oracle/_ref missing: run python -m oracle.build_ref "
+                               "where /root/reference exists)"}
+    import tempfile
+    out = {"device": torch.cuda.get_device_name(dev), "source": refshim.kind(),
+           "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+    try:
+        ref = refshim.load()
+        ref.model.Model._get_device = lambda self_: torch.device(dev)
+        with tempfile.TemporaryDirectory() as tmp:
+            path = synth.save_state_dict(0, os.path.join(tmp, "mRNA_model_RNA004.pth"))
+            mdl = ref.model.Model(path, refshim.cnn_config(), logging.getLogger("reference"), "mRNA")
+        # --- batch 1, as control.py:69 calls it (float64 numpy in, tensor out, .item() like control.py:152)
+        rng = np.random.default_rng(0)
+        xs = [rng.standard_normal(L) for _ in range(8)]
+        for x in xs[:4]:
+            mdl.classify(x)[1].item()
+        n1 = 64
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(n1):
+            mdl.classify(xs[i % len(xs)])[1].item()
+        torch.cuda.synchronize(dev)
+        out["batch1"] = {"value": n1 / (time.perf_counter() - t0), "unit": UNIT,
+                         "what": f"reference Model.classify on cuda, one read of {L} samples per call, {n1} calls"}
+        # --- whole batch through cuDNN
+        X = torch.randn(B, L, device=dev, dtype=torch.float32)
+        net = mdl.model
+
+        def timed(fn):
+            with torch.no_grad():
+                for _ in range(2):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    fn()
+                b.record()
+                b.synchronize()
+            return B * iters / (a.elapsed_time(b) * 1e-3)
+
+        def fwd():
+            return torch.nn.functional.softmax(net(X), dim=1)
+
+        def fwd_bf16():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return torch.nn.functional.softmax(net(X), dim=1)
+
+        out["batched_tf32"] = {"value": timed(fwd), "unit": UNIT,
+                               "what": f"reference ConvNet(X[{B},{L}]) fp32 input, cuDNN convs with TF32 allowed"}
+        out["batched_bf16_autocast"] = {"value": timed(fwd_bf16), "unit": UNIT,
+                                        "what": "same under torch.autocast(bfloat16)"}
+        del X
+        torch.cuda.empty_cache()
+    except Exception as e:      # a baseline leg must never take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
+def run_reads(args, rank, local_rank, world):
+    """BASELINE config 4: R synthetic reads of 12,048 samples (RNA002), read r -> rank r mod G (riser_b200.shard), every
+    rank streams its shard through FixedBatchPipeline from HOST buffers in batches of `--batch`; per-read decisions are
+    gathered (the only exchange) and checked against decisions computed on ONE GPU for the same reads.  Strong scaling:
+    value = R / max-over-ranks device time."""
+    import torch.distributed as dist
+    from riser_b200 import Kit, SignalProcessor, Model, BatchedClassifier, FixedBatchPipeline, synth, shard
+    from riser_b200.config import shipped_config
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R, B, L = args.reads, args.batch, args.reads_length
+    log = logging.getLogger("bench")
+    mdl = Model(synth.state_dict(0), shipped_config(), log, "mRNA")
+    clf = BatchedClassifier([mdl], SignalProcessor(Kit.create_from_version("RNA002")))
+    clf.max_len, clf.ld = L, (L + 3) & ~3
+    # read r is pool[(r * 40503) % P]: any rank can name any read without holding a million of them
+    P = 509
+    pool = synth.body_batch(1234, P, L)
+    mine = shard.shard_indices(np.arange(R), rank, world)
+    n_batches = (len(mine) + B - 1) // B
+    hosts = []
+    for k in range(2):      # two pinned staging batches, refilled from the pool per step (the gather is host work
+        hosts.append(torch.empty(B, L, dtype=torch.int16).pin_memory())     # inside the timed region)
+    pipe = FixedBatchPipeline(clf, B, L, 0.9, "deplete")
+
+    def fill(k, host):
+        idx = mine[k * B:(k + 1) * B]
+        hv = host.numpy()
+        src = (idx * 40503) % P
+        hv[:len(idx)] = pool[src]
+        if len(idx) < B:
+            hv[len(idx):] = 0          # constant reads: classified, ignored at the gather
+        return len(idx)
+
+    for k in range(2):
+        fill(0, hosts[k])
+        pipe.result(pipe.submit(hosts[k]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dec_local = np.empty(len(mine), dtype=np.uint8)
+    pon_local = np.empty((len(mine), 1), dtype=np.float32)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    pipe.copy_stream.wait_event(e0)
+    tickets, counts = [], []
+    for k in range(n_batches):
+        counts.append(fill(k, hosts[k % 2]))
+        tickets.append(pipe.submit(hosts[k % 2]))
+        if k >= 1:
+            d, pr = pipe.result(tickets[k - 1])
+            n = counts[k - 1]
+            dec_local[(k - 1) * B:(k - 1) * B + n] = d[:n]
+            pon_local[(k - 1) * B:(k - 1) * B + n, 0] = pr[0, :n, 1]
+    if n_batches:
+        d, pr = pipe.result(tickets[-1])
+        n = counts[-1]
+        dec_local[(n_batches - 1) * B:(n_batches - 1) * B + n] = d[:n]
+        pon_local[(n_batches - 1) * B:(n_batches - 1) * B + n, 0] = pr[0, :n, 1]
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    host_s = time.perf_counter() - t_host0
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dec_all, pon_all, _ = shard.gather_decisions(mine, dec_local, pon_local, np.zeros(len(mine), np.int32), R)
+    else:
+        dec_all, pon_all = dec_local, pon_local
+    ms = float(t.cpu())
+    if rank == 0:
+        # single-GPU decisions of the same reads: classify the pool once on this GPU, map through the index rule
+        hp = torch.empty(B, L, dtype=torch.int16).pin_memory()
+        hp.numpy()[:P] = pool
+        hp.numpy()[P:] = 0
+        d_pool, _ = pipe.result(pipe.submit(hp))
+        expect = d_pool[:P][(np.arange(R) * 40503) % P]
+        agree = int((expect == dec_all).sum())
+        line = {"metric": METRIC, "value": R / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": n_batches,
+                "warmup": 2, "ms_per_step": ms / max(1, n_batches), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f16+e4m3", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[3]: {R} synthetic reads of {L} samples (RNA002), sharded by read "
+                                       f"r mod {world} across {world} B200, batches of {B} from host buffers",
+                           "cache": "inputs streamed from host every batch (24 KB per read H2D inside the timed region)"},
+                "e2e": {"value": R / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+                        "d2h_bytes_per_step": pipe.d2h_bytes},
+                "sharding": {"rule": "read r -> rank r mod G (riser_b200.shard.shard_indices)", "collective": "none on the "
+                             "data path; decisions gathered once (shard.gather_decisions, 9 B per read)",
+                             "decisions_equal_single_gpu": agree, "of": R,
+                             "host_gb_per_s_per_rank": len(mine) * L * 2 / host_s / 1e9,
+                             "host_note": "pinned-buffer fill (numpy gather from the read pool) + H2D per rank"},
+                "gpu_launches": n_batches * (1 + mdl.launches(B, L) + 1),
+                "clocks": sampler.summary()}
+        assert agree == R, f"sharded decisions differ from the single-GPU decisions: {agree} of {R} agree"
+        _emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def _emit(line):
@@ -207,9 +481,11 @@ def main():
     ap.add_argument("--length", type=int, default=LENGTH)
     ap.add_argument("--precision", type=int, default=None, help="0 F16, 1 F16_W2, 2 F16_X3, 3 F16_F8; default = riser_b200.model.DEFAULT_PRECISION")
     ap.add_argument("--chunk", type=int, default=None)
-    ap.add_argument("--ref-reads", type=int, default=1024, help="reads per step of the --impl reference arm (~2.6 s of CPU work)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="reads of the cpu_baseline leg (default: the whole batch, ~10 s)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-reads", type=int, default=128, help="reads per step of the --impl reference arm (~3 s of CPU work)")
+    ap.add_argument("--cpu-sample", type=int, default=384, help="reads of the cpu_baseline leg (the reference, all host threads; ~10 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side legs: cpu_baseline, torch_cuda_baseline, latency")
+    ap.add_argument("--reads", type=int, default=0, help="BASELINE config 4: this many reads sharded r mod G (separate line)")
+    ap.add_argument("--reads-length", type=int, default=12048)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -218,6 +494,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.reads:
+        run_reads(args, rank, local_rank, world)
         return
 
     import torch.distributed as dist
@@ -322,6 +601,28 @@ def main():
     e2e_ms = e2e_start.elapsed_time(e2e_end)
     barrier()
     dec_host = torch.from_numpy(dec_np.copy())
+    # ---- the same chunks through the call RISER's loop makes: BatchedClassifier.classify_batch with a list of
+    #      UNPINNED numpy arrays (np.frombuffer views in the live run) -> native gather into the pinned arena -> H2D ->
+    #      poly(A) detection + gating (control.py:36-60: these 16,000-sample prefixes have no poly(A), so the fixed trim
+    #      cuts them to the kit's max length) -> normalise -> network -> decide -> D2H, one host sync per call.
+    live_api = None
+    if world == 1:
+        sig_list = [np.array(hv[i]) for i in range(B)]          # pageable copies
+        ids = [f"r{i}" for i in range(B)]
+        live_clf = BatchedClassifier([mdl], proc, chunk=args.chunk)
+        for _ in range(3):
+            r_live = live_clf.classify_batch(sig_list, ids, {}, 0.9, "deplete")
+        n_live = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_live):
+            r_live = live_clf.classify_batch(sig_list, ids, {}, 0.9, "deplete")
+        dt_live = time.perf_counter() - t0
+        live_api = {"value": B * n_live / dt_live, "unit": UNIT, "ms_per_call": dt_live / n_live * 1e3,
+                    "h2d_bytes_per_step": int(r_live.h2d_bytes), "d2h_bytes_per_step": int(r_live.d2h_bytes),
+                    "classified_samples_per_read": int(r_live.sig_len.max()),
+                    "api": "BatchedClassifier.classify_batch(list of unpinned int16 arrays): host gather + H2D + poly(A) "
+                           "detection + gating + normalise + network + decide + D2H; wall clock, no overlap between calls"}
+        del live_clf
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -344,28 +645,36 @@ def main():
             with open(tpath) as f:
                 traffic = json.load(f).get(f"B{B}_L{L}_p{precision}")
         launches_per_step = 1 + mdl.launches(B, L, clf.chunk) + 1
+        f8_from = int(os.environ.get("RISER_F8_FROM", "6"))
+        peq = pass_equivalents(L, precision, f8_from)
+        tsrc = None
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tsrc = json.load(f).get("_source")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f16", 1: "f16", 2: "f16", 3: "f16+e4m3"}[precision],
             "data": "synthetic",
-            "config": {"workload": workload_name(B, L), "precision_mode": precision,
-                       "arithmetic": {0: "f16 operands, f32 accumulate (1 tcgen05 pass)",
-                                      1: "f16, weights split hi+lo (2 passes), f32 accumulate",
-                                      2: "f16, weights and activations split hi+lo (3 passes), f32 accumulate",
-                                      3: "f16 pass + e4m3 correction pass carrying the hi/lo terms (2 pass-equivalents; "
-                                         "layers 1-5 as mode 2), f32 accumulate; layer 0 and the head in f32, "
-                                         "normalise in f64"}[precision],
-                       "chunk": clf.chunk,
-                       "cache": "L2 flushed between steps (256 MiB write); inputs 393 MB > L2",
-                       "flops_per_read": flops_per_read(L), "decisions_made": n_dec},
-            "roofline": {"bound": "tensor", "kernel": "fused01_kernel + conv_tc_kernel (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
+            "config": shared_config(B, L),
+            "arm": {"precision_mode": precision,
+                    "arithmetic": {0: "f16 operands, f32 accumulate (1 tcgen05 pass)",
+                                   1: "f16, weights split hi+lo (2 passes), f32 accumulate",
+                                   2: "f16, weights and activations split hi+lo (3 passes), f32 accumulate",
+                                   3: "f16 pass + e4m3 correction pass carrying the hi/lo terms (2 pass-equivalents; "
+                                      "layers 1-5 as mode 2), f32 accumulate; layer 0 and the head in f32, "
+                                      "normalise in f64"}[precision],
+                    "chunk": clf.chunk, "decisions_made": n_dec},
+            "roofline": {"bound": "tensor", "kernel": "fused01_kernel + conv_eo_kernel x3 + conv_tc_kernel x7 (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                         "traffic": traffic, "peak_source": f"bf16_tflops_sustained, {peak_src}",
-                         "executed_tflops": achieved * {0: 1, 1: 2, 2: 3, 3: 2}[precision],
-                         "executed_note": "fp16-pass-equivalents of tcgen05 work per algorithmic FLOP: 1 (F16), "
-                                          "2 (F16_W2), 3 (F16_X3), 2 (F16_F8: one fp16 pass + two e4m3 passes at twice the rate)",
+                         "traffic": traffic, "traffic_source": tsrc, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                         "frac_burst": achieved / burst_peak(), "peak_burst": burst_peak(),
+                         "pass_equivalents": peq, "ceiling": 1.0 / peq,
+                         "ceiling_note": "1 / fp16-pass-equivalents executed per algorithmic FLOP: what frac would be at a "
+                                         "perfect tensor pipe with this precision scheme (single-pass fp16/tf32 misses "
+                                         "the 1e-3 probability bar, DESIGN.md section 2)",
+                         "executed_tflops": achieved * peq,
                          "share_of_step": conv_ms / (total_ms / args.steps)},
             "roofline_normalise": {"bound": "hbm", "kernel": "normalise_kernel", "achieved": 6 * L * B / norm_ms / 1e6,
                                    "peak": hbm_peak, "unit": "GB/s", "frac": 6 * L * B / norm_ms / 1e6 / hbm_peak,
@@ -373,17 +682,24 @@ def main():
                                    "peak_source": f"hbm_gbs, {peak_src}"},
             "e2e": {"value": reads / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
-                    "overlap": "H2D of step k+1 overlaps kernels of step k (2 slots)"},
+                    "overlap": "H2D of step k+1 overlaps kernels of step k (2 slots)",
+                    "api": "FixedBatchPipeline.submit / result (pinned [B, L] int16 in, decisions + probabilities out)"},
             "gpu_launches": launches_per_step * args.steps * 2,
             "clocks": sampler.summary(),
         }
+        if live_api is not None:
+            line["e2e_live_api"] = live_api
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            X = cpu_reads(args.cpu_sample, L)
-            v = time_cpu_path(X, synth.state_dict(0), cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} reads of {L} samples, per-read loop "
-                                              "(oracle normalise + torch-CPU ConvNet), torch threads = cores"}
+            line["cpu_baseline"] = cpu_baseline(L, args.cpu_sample, 1024, 48)
+            line["torch_cuda_baseline"] = torch_cuda_baseline(host, dev, B, L)
+            try:
+                from riser_b200 import sim
+                line["latency"] = {"what": "ms per poll, batch in hand -> decisions on host (BASELINE config 5; "
+                                           "riser_b200.sim.measure_latency, 1 s of new signal per channel and poll)",
+                                   "minion_512ch_2models": sim.measure_latency(512, 80, "RNA002", ("mRNA", "mtRNA")),
+                                   "promethion_3000ch_1model": sim.measure_latency(3000, 60, "RNA002", ("mRNA",))}
+            except Exception as e:
+                line["latency"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

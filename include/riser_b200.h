@@ -105,6 +105,15 @@ int riser_normalise_f32_max_len(void);
 int riser_normalise_f32(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
                         float outlier_lim, float* out, int64_t ld_out, riser_stream_t stream);
 
+/* The live path's SignalProcessor.mad_normalise (riser/preprocess.py:108-147) for float32 input -- the
+ * secondary input mode (calibrated signal): numpy keeps float32 throughout there too
+ * (np.median, np.vectorize over float32 scalars), so the arithmetic is that of riser_normalise_f32 with
+ * the outlier limit 3.5 and WITH the MAD == 0 guard of preprocess.py:122-124 (all-zero output).
+ * med_mad (optional, may be NULL): float32 [B,2] = {median, MAD}, so the host mirror can return the
+ * reference's int64 zeros when MAD == 0.                                                         */
+int riser_normalise_f32_live(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
+                             float* out, int64_t ld_out, float* med_mad, riser_stream_t stream);
+
 /* Replaces SignalProcessor.get_polyA_end (riser/preprocess.py:42-79), batched.
  * Read b is sig[off[b] .. off[b] + n[b]).  polya_end[b] = the returned window
  * start index, or -1 for None.  Window statistics are exact integers; the

@@ -8,6 +8,7 @@ gate -> normalise -> classify -> decide (control.py:31-93); here the whole poll 
 ``BatchedClassifier.classify_batch`` once, the decision codes come back as one array, and the rows and the
 three read lists are cut out of that array.
 """
+import collections
 import time
 
 import numpy as np
@@ -18,6 +19,7 @@ CSV_HEADER = 'batch_start,read_id,channel,sig_length,models,prob_targets,thresho
 TAKE_OVER_NOTICE = ('The sequencing run is being controlled by RISER, reads that are '
                     'not in the target class will be ejected from the pore.')                         # control.py:13-14
 PROGRESS_PERIOD_S = 60                                                                                # control.py:19,116
+LATENCY_HISTORY = 4096       # polls whose latency / size SequencerControl remembers
 
 
 class _MinuteTally:
@@ -60,8 +62,11 @@ class SequencerControl():
         self.out_filename = out_file
         self.classifier = BatchedClassifier(models, processor)
         self.warm_up_batches = tuple(warm_up_batches)
-        self.batch_latencies = []      # seconds from "batch in hand" to "decisions on host"
-        self.batch_sizes = []
+        # Instrumentation (additive): seconds from "batch in hand" to "decisions on host" and the batch size of
+        # the most recent non-empty polls.  Bounded -- ReadUntil's get_read_chunks does not block, so an idle
+        # client is polled tens of thousands of times a second and a run lasts days.
+        self.batch_latencies = collections.deque(maxlen=LATENCY_HISTORY)
+        self.batch_sizes = collections.deque(maxlen=LATENCY_HISTORY)
 
     # ------------------------------------------------------------------ riser.py's three calls
     def start(self):
@@ -96,6 +101,13 @@ class SequencerControl():
     def _poll(self, sink, tally, polyA_cache, model_names, mode, threshold, unblock_duration):
         batch_start = time.monotonic()
         batch = list(self.client.get_read_batch())
+        if not batch:
+            # nothing arrived: the reference's loop body does not run and its two client calls get empty lists
+            # (control.py:100-106); no device work, nothing recorded
+            self.client.reject_reads([], unblock_duration)
+            self.client.finish_processing_reads([])
+            tally.maybe_report(batch_start)
+            return
         signals = [self.client.get_raw_signal(read) for _, read in batch]
         t0 = time.monotonic()
         res = self.classifier.classify_batch(signals, [read.id for _, read in batch], polyA_cache, threshold, mode)

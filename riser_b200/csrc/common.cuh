@@ -56,6 +56,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// 32-byte global store (STG.256, sm_100): `p` 32-byte aligned.  One full L2 sector per lane and request --
+// two 16-byte stores to the same sector are two half-filled sector writes and two tag look-ups at the L2,
+// which is what bounded the narrow layers (profiles/README.md, round 2).
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+#ifdef RISER_ST128   // A/B timing builds: the two 16-byte stores this replaces
+  reinterpret_cast<uint4*>(p)[0] = a;
+  reinterpret_cast<uint4*>(p)[1] = b;
+  return;
+#endif
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 namespace riser {
@@ -371,9 +372,7 @@ __device__ __forceinline__ void epilogue_row16(const uint32_t (&ve)[16], const u
   __half2 hv[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
-  uint4* oh = reinterpret_cast<uint4*>(ohi);
-  oh[0] = *reinterpret_cast<const uint4*>(hv);
-  oh[1] = *reinterpret_cast<const uint4*>(hv + 4);
+  st_global_256(ohi, *reinterpret_cast<const uint4*>(hv), *reinterpret_cast<const uint4*>(hv + 4));
   if (lo_off) {
     __half2 lv[8];
 #pragma unroll
@@ -386,8 +385,7 @@ __device__ __forceinline__ void epilogue_row16(const uint32_t (&ve)[16], const u
 #else
     uint4* ol = reinterpret_cast<uint4*>(ohi + lo_off);
 #endif
-    ol[0] = *reinterpret_cast<const uint4*>(lv);
-    ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
+    st_global_256(ol, *reinterpret_cast<const uint4*>(lv), *reinterpret_cast<const uint4*>(lv + 4));
   }
   if (f8) store_f8_planes<16>(r, hv, f8, f8_stride);
 }
@@ -1384,9 +1382,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
           __half2 hv[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
-          uint4* oh = reinterpret_cast<uint4*>(orow + c16 * 16);
-          oh[0] = *reinterpret_cast<const uint4*>(hv);
-          oh[1] = *reinterpret_cast<const uint4*>(hv + 4);
+          st_global_256(orow + c16 * 16, *reinterpret_cast<const uint4*>(hv), *reinterpret_cast<const uint4*>(hv + 4));
           if (lo_off) {
             __half2 lv[8];
 #pragma unroll
@@ -1394,9 +1390,8 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
               const float2 back = __half22float2(hv[c]);
               lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
             }
-            uint4* ol = reinterpret_cast<uint4*>(orow + lo_off + c16 * 16);
-            ol[0] = *reinterpret_cast<const uint4*>(lv);
-            ol[1] = *reinterpret_cast<const uint4*>(lv + 4);
+            st_global_256(orow + lo_off + c16 * 16, *reinterpret_cast<const uint4*>(lv),
+                          *reinterpret_cast<const uint4*>(lv + 4));
           }
           if (a.out_f8)
             store_f8_planes<16>(r, hv, reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c16 * 16, a.cout_p);
@@ -2117,6 +2112,12 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   RISER_REQUIRE(precision >= RISER_PREC_F16 && precision <= RISER_PREC_F16_F8,
                 "riser_model_create: unknown precision %d", precision);
   RISER_REQUIRE(channels[0] <= 64, "riser_model_create: layer 0 supports at most 64 output channels");
+  // the caller's current device is left as it was (several models / GPUs per process: shard.py)
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  RISER_CUDA_TRY(cudaGetDevice(&guard.prev));
   RISER_CUDA_TRY(cudaSetDevice(device));
   int major = 0;
   RISER_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -2225,7 +2226,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
   RISER_REQUIRE(out && m && workspace, "riser_plan_create: null pointer");
   RISER_REQUIRE(B > 0 && max_len >= kMinLen, "riser_plan_create: need B > 0 and max_len >= %d", kMinLen);
   RISER_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "riser_plan_create: workspace not 256-byte aligned");
-  riser_plan* p = new riser_plan();
+  std::unique_ptr<riser_plan, int (*)(riser_plan*)> owner(new riser_plan(), riser_plan_destroy);   // freed on every error return
+  riser_plan* p = owner.get();
   p->model = m;
   p->B = B;
   p->max_len = max_len;
@@ -2235,7 +2237,6 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
   plan_lengths(m, max_len, p->Lmax, p->Lp);
   const size_t need = plan_offsets(m, B, p->Lp, p->act_off);
   if (workspace_bytes < need) {
-    delete p;
     return fail(RISER_ENOMEM, "riser_plan_create: workspace %zu < %zu bytes", workspace_bytes, need);
   }
   RISER_REQUIRE(static_cast<int64_t>(B) * p->Lp[1] * 8 < (int64_t(1) << 31), "riser_plan_create: B * L too large");
@@ -2308,10 +2309,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.tm_a8 = lp.tm_a;
       lp.tm_b8 = lp.tm_b;
     }
-    if (st) {
-      delete p;
-      return st;
-    }
+    if (st) return st;
     ConvArgs& a = lp.args;
     std::memset(&a, 0, sizeof(a));
     a.bias = L.bias;
@@ -2420,10 +2418,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       const uint64_t pitch = static_cast<uint64_t>(L.cin_p) * m->act_planes;     // fp16 elements per row
       int st2 = make_tmap(&lp.tm_a, p->ws + p->act_off[i], pitch, n_pairs, 136, true);
       if (!st2) st2 = make_tmap(&lp.tm_a8, p->ws + p->act_off[i] + n_pairs * pitch * 2, pitch, n_pairs, 136, true);
-      if (st2) {
-        delete p;
-        return st2;
-      }
+      if (st2) return st2;
       a.acc_cols = round_up(2 * L.n_tile, 32);
       const size_t w_eo = static_cast<size_t>(L.passes) * a.k_blocks * 3 * b_bytes;
       const size_t group1 = static_cast<size_t>(m->act_planes) * 2 * kEoTile;
@@ -2440,10 +2435,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.pair = 1;
       int st2 = make_tmap(&lp.tm_b, L.w, L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
       if (!st2) st2 = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
-      if (st2) {
-        delete p;
-        return st2;
-      }
+      if (st2) return st2;
       a.idesc = umma_idesc_f16(256, L.n_tile);
       a.ms = (2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 2) >= 2) ? 2 : 1;
       const size_t a_group = static_cast<size_t>(a.ms) * 136 * 128, half_b = static_cast<size_t>(L.n_tile / 2) * 128;
@@ -2497,7 +2489,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       for (int res = 0; res < 2; ++res)
         RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_kernel(ms, 1, 1, res, 0, k32v, 1)),
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  *out = p;
+  *out = owner.release();
   return RISER_OK;
 }
 

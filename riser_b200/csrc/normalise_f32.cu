@@ -123,7 +123,8 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 
 __global__ void __launch_bounds__(kThreads)
 normalise_f32_kernel(const float* __restrict__ sig, const int64_t* __restrict__ off, const int32_t* __restrict__ len,
-                     int B, float lim, float* __restrict__ out, int64_t ld_out) {
+                     int B, float lim, float* __restrict__ out, int64_t ld_out, int zero_if_mad0,
+                     float* __restrict__ med_mad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Scratch& s = *reinterpret_cast<Scratch*>(smem_raw);
   float* x = reinterpret_cast<float*>(smem_raw + ((sizeof(Scratch) + 15) & ~size_t(15)));
@@ -143,6 +144,15 @@ normalise_f32_kernel(const float* __restrict__ sig, const int64_t* __restrict__ 
     select_middle([&](int i) { return __float_as_uint(fabsf(__fsub_rn(x[i], med))); }, n, k1, k2, s, a1, a2);
     const float mad = (k1 == k2) ? __uint_as_float(a1)
                                  : __fmul_rn(__fadd_rn(__uint_as_float(a1), __uint_as_float(a2)), 0.5f);
+    if (med_mad && tid == 0) {
+      med_mad[2 * b] = med;
+      med_mad[2 * b + 1] = mad;
+    }
+    if (zero_if_mad0 && mad == 0.f) {          // the live path's guard (riser/preprocess.py:122-124)
+      for (int i = tid; i < n; i += kThreads) o[i] = 0.f;
+      __syncthreads();
+      continue;
+    }
     const float denom = __fmul_rn(1.4826f, mad);                       // preprocess.py:44
     auto norm = [&](int i) { return __fdiv_rn(__fsub_rn(x[i], med), denom); };
     auto clip = [&](float v) { return v > lim ? lim : (v < -lim ? -lim : v); };
@@ -170,17 +180,17 @@ normalise_f32_kernel(const float* __restrict__ sig, const int64_t* __restrict__ 
 }  // namespace
 }  // namespace riser
 
-using namespace riser;
+extern "C" int riser_normalise_f32_max_len(void) { return riser::kMaxLenF32; }
 
-extern "C" int riser_normalise_f32_max_len(void) { return kMaxLenF32; }
-
-extern "C" int riser_normalise_f32(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
-                                   float outlier_lim, float* out, int64_t ld_out, riser_stream_t stream) {
-  RISER_REQUIRE(B >= 0, "riser_normalise_f32: B < 0");
+namespace riser {
+namespace {
+int launch_f32(const char* who, const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
+               float outlier_lim, int zero_if_mad0, float* out, int64_t ld_out, float* med_mad, riser_stream_t stream) {
+  RISER_REQUIRE(B >= 0, "%s: B < 0", who);
   if (B == 0) return RISER_OK;
-  RISER_REQUIRE(sig && off && len && out, "riser_normalise_f32: null pointer");
+  RISER_REQUIRE(sig && off && len && out, "%s: null pointer", who);
   RISER_REQUIRE(max_len > 0 && max_len <= kMaxLenF32 && ld_out >= max_len,
-                "riser_normalise_f32: max_len %d outside (0, %d] or ld_out too small", max_len, kMaxLenF32);
+                "%s: max_len %d outside (0, %d] or ld_out too small", who, max_len, kMaxLenF32);
   const size_t smem = ((sizeof(Scratch) + 15) & ~size_t(15)) + 4 * static_cast<size_t>(max_len);
   RISER_CUDA_TRY(cudaFuncSetAttribute(normalise_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
@@ -189,7 +199,20 @@ extern "C" int riser_normalise_f32(const float* sig, const int64_t* off, const i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normalise_f32_kernel, kThreads, smem);
   const int grid = std::min(B, sms * std::max(1, per_sm));
-  normalise_f32_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, len, B, outlier_lim, out, ld_out);
+  normalise_f32_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(sig, off, len, B, outlier_lim, out, ld_out,
+                                                                    zero_if_mad0, med_mad);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
+}
+}  // namespace
+}  // namespace riser
+
+extern "C" int riser_normalise_f32(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
+                                   float outlier_lim, float* out, int64_t ld_out, riser_stream_t stream) {
+  return riser::launch_f32("riser_normalise_f32", sig, off, len, B, max_len, outlier_lim, 0, out, ld_out, nullptr, stream);
+}
+
+extern "C" int riser_normalise_f32_live(const float* sig, const int64_t* off, const int32_t* len, int B, int max_len,
+                                        float* out, int64_t ld_out, float* med_mad, riser_stream_t stream) {
+  return riser::launch_f32("riser_normalise_f32_live", sig, off, len, B, max_len, 3.5f, 1, out, ld_out, med_mad, stream);
 }

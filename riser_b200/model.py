@@ -187,6 +187,8 @@ class Model():
         max_len = int(max_len if max_len is not None else x.shape[1])
         if probs is None:
             probs = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+        if B == 0:
+            return probs
         chunk = int(chunk or DEFAULT_CHUNK or B)
         L = _lib.lib()
         stream = _lib.stream_ptr()
@@ -226,6 +228,8 @@ class Model():
 
     def launches(self, B, max_len, chunk=None):
         """Kernels one classify_batch call launches."""
+        if B <= 0:
+            return 0
         chunk = int(chunk or DEFAULT_CHUNK or B)
         return sum(self.plan(min(chunk, B - lo), max_len).launches for lo in range(0, B, chunk))
 

@@ -123,6 +123,24 @@ class BatchedClassifier:
                                          _lib.ptr(buf["len"]), _lib.stream_ptr()), "riser_select_window")
         return buf["start"], buf["len"], buf["detected"]
 
+    @staticmethod
+    def _as_int16(signals):
+        """The batched path packs raw int16 ADC samples (riser/client.py:47: np.frombuffer(raw_data, signal_dtype)
+        with the ReadUntil default, uncalibrated signal).  The dtype is looked at once per poll, on the first
+        non-empty read: other integer dtypes are converted, a client configured for calibrated (float) signal is
+        refused -- packing float bytes as int16 would classify garbage silently."""
+        for s in signals:
+            if len(s):
+                dt = getattr(s, "dtype", None)
+                if dt == np.int16:
+                    return signals
+                if dt is not None and dt.kind in "iu":
+                    return [np.ascontiguousarray(x, dtype=np.int16) for x in signals]
+                raise TypeError(f"BatchedClassifier.classify_batch needs raw int16 signal, got {dt}: run the "
+                                "ReadUntil client with calibrated_signal=False (the default), or use "
+                                "SignalProcessor.mad_normalise + Model.classify for float signal")
+        return signals
+
     # ------------------------------------------------------------------ public entry
     def classify_batch(self, signals, read_ids, polyA_cache, threshold, mode):
         """One pass of riser/control.py:31-97 over a batch.
@@ -142,6 +160,7 @@ class BatchedClassifier:
             res.h2d_bytes = res.d2h_bytes = 0
             return res
         n_real = B
+        signals = self._as_int16(signals)
         B = bucket_size(n_real)                       # pad with empty reads up to the bucket
         cached = np.full(B, -1, dtype=np.int32)
         cached[:n_real] = np.fromiter((polyA_cache.get(r, -1) for r in read_ids), dtype=np.int32, count=n_real)

@@ -210,17 +210,58 @@ class SignalProcessor():
 
     # ------------------------------------------------------------ normalise
     def mad_normalise(self, signal):
-        """riser/preprocess.py:108-115: float64 ndarray out (the GPU result is the
-        reference's float64 value rounded to fp32 -- the cast riser/model.py:25
-        applies anyway -- widened back to float64).  Raises ValueError on empty."""
+        """riser/preprocess.py:108-115.  Raises ValueError on empty input.
+
+        int16 (what ``client.get_raw_signal`` hands over, riser/client.py:47), any other integer dtype and
+        float64 holding integers in the int16 range: numpy works in float64 there and so does ``riser_normalise``
+        -- the float64 ndarray returned is the reference's result rounded to fp32 (the cast riser/model.py:25
+        applies anyway).  float32 (calibrated signal, the secondary input mode): numpy keeps float32 for the
+        median, the MAD, the division and the smoothing, and ``riser_normalise_f32_live`` reproduces that bit
+        for bit; a float32 ndarray is returned, as the reference does.  Non-integral float64 takes the float32
+        route (1e-7-relative, inside the 1e-6 bar; the reference would stay in float64).  MAD == 0 returns
+        int64 zeros like the reference (``np.vectorize`` types its output by the first element, the int 0 of
+        preprocess.py:123)."""
         signal = np.asarray(signal)
-        if signal.shape[0] == 0:
+        if signal.ndim != 1:
+            raise ValueError(f"expected a 1-D signal, got shape {signal.shape}")
+        n = signal.shape[0]
+        if n == 0:
             raise ValueError("Signal must not be empty")
         if signal.dtype != np.int16:
-            raise TypeError("riser_b200 normalises raw int16 ADC signal (riser/client.py:47); "
-                            f"got {signal.dtype}")
-        out, _ = self.mad_normalise_batch([signal])
-        return out[0, :signal.shape[0]].double().cpu().numpy()
+            as16 = None
+            if signal.dtype.kind in "iub":
+                if signal.min() >= -32768 and signal.max() <= 32767:
+                    as16 = signal.astype(np.int16)
+            elif signal.dtype == np.float64:
+                r = np.rint(signal)
+                if np.array_equal(r, signal) and r.min() >= -32768 and r.max() <= 32767:
+                    as16 = r.astype(np.int16)
+            elif signal.dtype.kind != "f":
+                raise TypeError(f"cannot normalise a signal of dtype {signal.dtype}")
+            if as16 is None:
+                return self._mad_normalise_f32(signal.astype(np.float32))
+            signal = as16
+        out, _, stats = self.mad_normalise_batch([signal], return_stats=True)
+        if int(stats[0, 1]) == 0:                      # 4 * MAD
+            return np.zeros(n, dtype=np.int64)
+        return out[0, :n].double().cpu().numpy()
+
+    def _mad_normalise_f32(self, signal):
+        device = _lib.require_device()
+        n = signal.shape[0]
+        if n > _lib.lib().riser_normalise_f32_max_len():
+            raise ValueError(f"signal of {n} samples exceeds riser_normalise_f32_max_len()")
+        sig = torch.from_numpy(np.ascontiguousarray(signal)).to(device)
+        off = torch.tensor([0, n], dtype=torch.int64, device=device)
+        ln = torch.tensor([n], dtype=torch.int32, device=device)
+        out = torch.empty(1, n, dtype=torch.float32, device=device)
+        med_mad = torch.empty(1, 2, dtype=torch.float32, device=device)
+        _lib.check(_lib.lib().riser_normalise_f32_live(_lib.ptr(sig), _lib.ptr(off), _lib.ptr(ln), 1, n,
+                                                       _lib.ptr(out), out.stride(0), _lib.ptr(med_mad),
+                                                       _lib.stream_ptr()), "riser_normalise_f32_live")
+        if float(med_mad[0, 1]) == 0.0:
+            return np.zeros(n, dtype=np.int64)
+        return out[0].cpu().numpy()
 
     def mad_normalise_batch(self, signals, start=None, length=None, out=None, return_stats=False):
         """Batched mad_normalise over ragged int16 windows.

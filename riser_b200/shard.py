@@ -27,9 +27,12 @@ def gather_decisions(local_idx, decisions, p_on, sig_len, n_total, group=None):
     on the data path itself."""
     world = dist.get_world_size(group)
     M = p_on.shape[1] if p_on.ndim == 2 else 1
-    counts = torch.zeros(world, dtype=torch.int64)
+    # NCCL moves device memory only: stage the (tiny) payload on this rank's GPU there
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
     counts[dist.get_rank(group)] = len(local_idx)
     dist.all_reduce(counts, group=group)
+    counts = counts.cpu()
     cap = int(counts.max())
     pack = torch.zeros(cap, 3 + M, dtype=torch.float64)
     n = len(local_idx)
@@ -38,8 +41,10 @@ def gather_decisions(local_idx, decisions, p_on, sig_len, n_total, group=None):
         pack[:n, 1] = torch.from_numpy(np.asarray(decisions, dtype=np.float64))
         pack[:n, 2] = torch.from_numpy(np.asarray(sig_len, dtype=np.float64))
         pack[:n, 3:] = torch.from_numpy(np.asarray(p_on, dtype=np.float64).reshape(n, M))
+    pack = pack.to(dev)
     bufs = [torch.zeros_like(pack) for _ in range(world)]
     dist.all_gather(bufs, pack, group=group)
+    bufs = [b.cpu() for b in bufs]
     out_dec = np.full(n_total, 4, dtype=np.uint8)          # SKIPPED
     out_p = np.zeros((n_total, M), dtype=np.float32)
     out_len = np.zeros(n_total, dtype=np.int32)

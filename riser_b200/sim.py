@@ -114,3 +114,38 @@ class LiveSimClient(SimClient):
             batch.append((c, SimRead(f"{rid}#{number}", number, sig[:n].tobytes())))
             self.state[c][1] = n + self.chunk
         return batch
+
+
+def measure_latency(channels, polls, kit_version="RNA002", targets=("mRNA",), seed=7, skip=5, pool_reads=None,
+                    precision=None):
+    """BASELINE config 5: ``channels`` pores, every poll each live read's prefix grows by one second of samples
+    (AccumulatingCache semantics, riser/client.py:29-31,44); the batched ``SequencerControl`` classifies every
+    poll.  Returns p50 / p99 of the time from "batch in hand" to "decisions on host" over the polls after the
+    first ``skip`` (the ReadUntil decision budget is ~1 s), with the run's counters."""
+    import logging
+    import os
+    import tempfile
+
+    from . import Kit, SignalProcessor, Model, SequencerControl, synth
+    from .config import shipped_config
+    log = logging.getLogger("riser_b200.sim")
+    kit = Kit.create_from_version(kit_version)
+    kw = {} if precision is None else {"precision": precision}
+    models = [Model(synth.state_dict(synth.TARGET_SEEDS[t]), shipped_config(), log, t, **kw) for t in targets]
+    n_pool = int(pool_reads or min(2 * channels, 2048))
+    reads = synth.raw_reads(seed, n_pool, min_body=14000, max_body=20000, frac_no_polya=0.05)
+    client = LiveSimClient(reads, channels, chunk=kit.sampling_hz, n_polls=polls, first_len=kit.sampling_hz)
+    with tempfile.TemporaryDirectory() as tmp:
+        control = SequencerControl(client, models, SignalProcessor(kit), log, os.path.join(tmp, "live"),
+                                   warm_up_batches=(channels,))
+        control.start()
+        control.target("deplete", 1, 0.9)
+        control.finish()
+        with open(os.path.join(tmp, "live.csv")) as f:
+            rows = sum(1 for _ in f) - 1
+    lat = np.array(control.batch_latencies) * 1e3
+    steady = lat[skip:] if len(lat) > skip + 3 else lat
+    return {"channels": int(channels), "models": len(targets), "kit": kit_version, "polls": int(len(lat)),
+            "p50_ms": round(float(np.median(steady)), 3), "p99_ms": round(float(np.percentile(steady, 99)), 3),
+            "max_ms": round(float(steady.max()), 3), "batch_size_median": int(np.median(control.batch_sizes)),
+            "assessed_rows": rows, "rejected": len(client.unblocked), "finished": len(client.finished)}

@@ -62,7 +62,7 @@ def test_loop_rows_calls_and_messages(tmp_path, monkeypatch, caplog):
     assert client.unblocked == [(4, 4)]                              # (channel, read.number): minknow-api <= v5
     assert client.finished == [(4, 4), (1, 1), (3, 3)]               # rejects, then accepts, then undecided
     assert control.classifier.seen == [["read-0", "read-1", "read-2", "read-3"], ["read-0", "read-1", "read-2"]]
-    assert control.batch_sizes == [4, 3] and len(control.batch_latencies) == 2
+    assert list(control.batch_sizes) == [4, 3] and len(control.batch_latencies) == 2
     assert client.messages[0].startswith("The sequencing run is being controlled by RISER")
     assert client.messages[-1] == "RISER has stopped running."
     text = caplog.text
@@ -91,3 +91,41 @@ def test_minute_tally_and_read_ids_without_number(tmp_path, monkeypatch, caplog)
     assert caplog.text.count("In the last minute") == 1
     assert "In the last minute 4 signals were assessed, 1 were accepted and 1 were rejected" in caplog.text
     assert client.unblocked == [(4, "r3")] and client.finished == [(4, "r3"), (1, "r0"), (3, "r2")]   # minknow-api >= v6
+
+
+def test_idle_polls_keep_no_state_and_history_is_bounded(tmp_path, monkeypatch):
+    """ReadUntil's get_read_chunks does not block: an idle client is polled tens of thousands of times a second for
+    days.  Empty polls must not touch the classifier or grow anything; the latency history is a bounded window; the
+    client still sees the reference's two calls with empty lists (control.py:100-106)."""
+    class _Idle(sim.SimClient):
+        def __init__(self, n_polls):
+            super().__init__([], chunk=1000, n_polls=n_polls)
+            self.calls = 0
+
+        def get_read_batch(self):
+            self.poll += 1
+            return []
+
+        def reject_reads(self, reads, unblock_duration):
+            assert reads == []
+            self.calls += 1
+
+        def finish_processing_reads(self, reads):
+            assert reads == []
+            self.calls += 1
+
+    class _Never:
+        def __init__(self, *a, **k):
+            pass
+
+        def classify_batch(self, *a, **k):
+            raise AssertionError("an empty poll reached the classifier")
+
+    monkeypatch.setattr(ctl_mod, "BatchedClassifier", _Never)
+    client = _Idle(5000)
+    control = ctl_mod.SequencerControl(client, [_Model("mRNA")], None, logging.getLogger("idle"), str(tmp_path / "idle"))
+    control.start()
+    control.target("deplete", 1, 0.9)
+    assert client.calls == 2 * 5000
+    assert len(control.batch_latencies) == 0 and len(control.batch_sizes) == 0
+    assert control.batch_latencies.maxlen == ctl_mod.LATENCY_HISTORY == control.batch_sizes.maxlen
