@@ -219,6 +219,33 @@ int riser_decide(const float* probs, const int32_t* len, int B, int M, float thr
  * Generic fp32 building blocks on CUDA cores, channel-last activations [B][L_pad][C], per-read
  * valid lengths; BatchNorm is folded into w / bias by the host (riser_b200/resnet.py).      */
 
+/* The stem in one launch: Conv1d(1 -> C, K, stride, padding) + folded BatchNorm + ReLU + MaxPool1d(2, 2, padding 1)
+ * (resnet.py:79-84).  x: fp32 [B][ld_x] normalised signal; w [K][Cp], bias [Cp] (Cp = channels padded to 4, zeros in
+ * the padding); len_conv / len_out: valid lengths after the convolution / after the pool; out [B][Lout_pad][Cp].   */
+int riser_stem_pool_cl(const float* x, int64_t ld_x, const int32_t* len_in, const float* w, const float* bias,
+                       float* out, const int32_t* len_conv, const int32_t* len_out, int B, int Lout_pad, int Cp, int K,
+                       int stride, int pad, riser_stream_t stream);
+
+/* The ResNet blocks on the tensor pipe (tcgen05, fp16 hi + lo operand planes = three passes, fp32 accumulation
+ * in TMEM).  One entry point, two modes:
+ *   w2 == NULL  one conv_block of resnet.py:26-37: Conv1d(k = taps in {1, 3}, stride in {1, 2}, padding (k-1)/2)
+ *               with the BatchNorm folded in, + residual (optional, the output's layout) + ReLU (`relu`);
+ *   w2 != NULL  a whole BasicBlock (resnet.py:50-57 + ResidualBlock.forward, resnet.py:39-47):
+ *               out = ReLU(conv2(ReLU(conv1_stride(x))) + shortcut(x)); the shortcut is the 1x1 stride-s conv
+ *               `wsc` (accumulated into conv2's accumulator; bias2 = conv2 bias + shortcut bias), else
+ *               `residual` (= x for the identity shortcut), else nothing.  The intermediate stays on the SM.
+ * Activations: fp32 channel-last [B][L_pad][C_p], channels padded to a multiple of 8 (padding channels zero),
+ * 32-byte aligned; rows outside [0, len_in[b]) read as zero, rows >= len_out[b] are not written.
+ * Weights: host-packed operand images (riser_b200/resnet.py pack_tc_weights): fp16 [plane hi, lo][tap][K block of
+ * 32 channels][N rows][32] in the K-major SWIZZLE_64B layout, multiplied by a power of two whose inverse is
+ * inv_scale*.  n1 / n2: output channels padded to 16 (<= 256).  cmid_p: conv1's output channels (fused mode).
+ * riser_res_tc_smem: shared memory a shape needs, 0 if unsupported (the caller falls back to riser_conv1d_cl). */
+size_t riser_res_tc_smem(int cin_p, int cmid_p, int n1, int n2, int taps, int stride, int fused, int shortcut_conv);
+int riser_res_tc(const float* in, const int32_t* len_in, const int32_t* len_out, float* out, const float* residual,
+                 const void* w1, const void* w2, const void* wsc, const float* bias1, const float* bias2,
+                 float inv_scale1, float inv_scale2, int B, int Lin_pad, int Lout_pad, int cin_p, int cmid_p,
+                 int cout_p, int n1, int n2, int taps, int stride, int relu, riser_stream_t stream);
+
 /* Conv1d(Cin->Cout, K, stride, padding) [+ residual] [+ ReLU] -- resnet.py:26-43,79-81.
  * w is packed [K][Cin][Cout]; rows outside [0, len_in[b]) are zero padding; rows
  * t >= len_out[b] are not written.  residual (optional) has the output's layout.          */

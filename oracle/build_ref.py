@@ -2,7 +2,8 @@
 
 comprna/riser is pure Python, so "compiling the reference from its sources where they lie" is
 ``py_compile``: the modules of the read-classification path under /root/reference/riser are compiled to
-sourceless ``.pyc`` files in oracle/_ref/ (git-ignored, NOT gpurun-ignored: like a built .so it travels to the
+sourceless byte-code files (``.rbc`` = a .pyc under another suffix: gpurun's snapshot, like most sync tools, leaves
+``*.pyc`` behind) in oracle/_ref/ (git-ignored, NOT gpurun-ignored: like a built .so it travels to the
 GPU box, where /root/reference does not exist).  No reference source text enters the repository or its history;
 oracle/_ref/MANIFEST.json records the SHA-256 of every source file that was compiled.
 
@@ -25,6 +26,7 @@ REF_ROOT = os.environ.get("RISER_REFERENCE", "/root/reference")
 
 # module path under riser/ -> path under oracle/_ref/ (the reference uses flat imports: `from nets.cnn import ...`)
 MODULES = ["preprocess.py", "model.py", "control.py", "nets/cnn.py", "nets/resnet.py", "retrain/preprocess.py"]
+SUFFIX = ".rbc"
 CONFIGS = ["model/mRNA_config_RNA002_R9.4.1.yaml"]      # hyper-parameters only (riser/model/*.yaml:6-12)
 
 
@@ -36,7 +38,7 @@ def build(verbose=False):
                 "files": {}}
     for rel in MODULES:
         src = os.path.join(src_root, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + SUFFIX)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: what tracebacks show instead of a path that does not exist on the GPU box
         py_compile.compile(src, cfile=dst, dfile=f"<comprna/riser>/riser/{rel}", doraise=True, optimize=0)

@@ -19,7 +19,22 @@ def source_available():
 
 
 def built_available():
-    return os.path.exists(os.path.join(BUILT, "preprocess.pyc"))
+    return os.path.exists(os.path.join(BUILT, "preprocess.rbc"))
+
+
+def _load_built(name, rel):
+    """Import one byte-compiled reference module (oracle/_ref/<rel>.rbc) under the flat name the reference's own
+    import statements use (`import preprocess`, `from nets.cnn import ConvNet`)."""
+    import importlib.machinery
+    import importlib.util
+    if name in sys.modules:
+        return sys.modules[name]
+    loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(BUILT, rel + ".rbc"))
+    spec = importlib.util.spec_from_loader(name, loader)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def available():
@@ -55,12 +70,23 @@ def load():
     if not available():
         raise RuntimeError(f"reference present neither at {REF_ROOT} nor byte-compiled in {BUILT}")
     _stub_dead_imports()
-    path = os.path.join(REF_ROOT, "riser") if source_available() else BUILT
-    if path not in sys.path:
-        sys.path.insert(0, path)
-    import preprocess, model, control          # noqa: E401
-    from nets.cnn import ConvNet
-    from nets.resnet import ResNet
+    if source_available():
+        path = os.path.join(REF_ROOT, "riser")
+        if path not in sys.path:
+            sys.path.insert(0, path)
+        import preprocess, model, control          # noqa: E401
+        from nets.cnn import ConvNet
+        from nets.resnet import ResNet
+    else:
+        if "nets" not in sys.modules:
+            pkg = types.ModuleType("nets")
+            pkg.__path__ = []
+            sys.modules["nets"] = pkg
+        ConvNet = _load_built("nets.cnn", "nets/cnn").ConvNet
+        ResNet = _load_built("nets.resnet", "nets/resnet").ResNet
+        preprocess = _load_built("preprocess", "preprocess")
+        model = _load_built("model", "model")
+        control = _load_built("control", "control")
     return types.SimpleNamespace(preprocess=preprocess, model=model, control=control,
                                  ConvNet=ConvNet, ResNet=ResNet)
 
@@ -78,7 +104,7 @@ def load_retrain_preprocess():
         spec = importlib.util.spec_from_file_location(
             "riser_retrain_preprocess", os.path.join(REF_ROOT, "riser", "retrain", "preprocess.py"))
     else:
-        path = os.path.join(BUILT, "retrain", "preprocess.pyc")
+        path = os.path.join(BUILT, "retrain", "preprocess.rbc")
         spec = importlib.util.spec_from_loader(
             "riser_retrain_preprocess", importlib.machinery.SourcelessFileLoader("riser_retrain_preprocess", path))
     mod = importlib.util.module_from_spec(spec)

@@ -40,6 +40,9 @@ SIGNATURES = {
     "riser_plan_layer_info": (c_int, [c_void_p, c_int, P(c_i64), P(c_int), P(c_int), P(c_int), P(c_int)]),
     "riser_plan_layer_eo": (c_int, [c_void_p, c_int]),
     "riser_conv1d_cl": (c_int, [c_void_p] * 7 + [c_int] * 9 + [c_void_p]),
+    "riser_stem_pool_cl": (c_int, [c_void_p, c_i64] + [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    "riser_res_tc_smem": (c_size_t, [c_int] * 8),
+    "riser_res_tc": (c_int, [c_void_p] * 10 + [c_float, c_float] + [c_int] * 11 + [c_void_p]),
     "riser_len_chain": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "riser_maxpool1d_cl": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "riser_gap_linear_softmax": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),

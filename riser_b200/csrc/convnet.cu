@@ -109,6 +109,7 @@ struct ConvArgs {
   int out_planes, out_fp32;
   int a_stages, b_stages, acc_stages, resident;
   int epi_sets;           // epilogue warp sets (each = 4 warps covering the TMEM lane quadrants)
+  int dual;               // conv_tc_kernel, MS == 2: one MMA-issuing thread PER SUB-TILE (warp 1 and the last warp)
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
@@ -288,6 +289,7 @@ struct ConvSmem {
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t w_full;
   uint64_t tmem_full[kMaxAccStages];
+  uint64_t tmem_full_ms[kMaxAccStages][4];   // conv_tc_kernel: "accumulator complete" per stage AND sub-tile
   uint64_t tmem_empty[kMaxAccStages][4];     // per accumulator stage AND sub-tile: released as soon as drained
   uint32_t tmem_base;
   alignas(16) float bias[2][kMaxNTile];
@@ -440,7 +442,7 @@ struct ItemFlags {
 };
 
 template <int MS, int PLANES, int WPLANES, bool RESIDENT, bool FUSED = false, bool K32 = false, bool F8 = false>
-__global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : 64 + 128 * kMaxEpiSets, 1)
+__global__ void __launch_bounds__(FUSED ? kConvThreads + kCvtThreads : 96 + 128 * kMaxEpiSets, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_b8,
                const ConvArgs a) {
@@ -473,18 +475,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tma_prefetch_desc(&tm_a8);
       tma_prefetch_desc(&tm_b8);
     }
+    const uint32_t n_issuers = a.dual ? 2 : 1;     // every issuer commits to the operand "empty" barriers
     for (int i = 0; i < a.a_stages; ++i) {
       mbar_init(&s.a_full[i], FUSED ? kCvtThreads : 1);
-      mbar_init(&s.a_empty[i], 1);
+      mbar_init(&s.a_empty[i], n_issuers);
     }
     for (int i = 0; i < a.b_stages; ++i) {
       mbar_init(&s.b_full[i], 1);
-      mbar_init(&s.b_empty[i], 1);
+      mbar_init(&s.b_empty[i], n_issuers);
     }
     mbar_init(&s.w_full, 1);
     for (int i = 0; i < a.acc_stages; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      for (int ms = 0; ms < MS; ++ms) mbar_init(&s.tmem_empty[i][ms], 4 * a.epi_sets);
+      for (int ms = 0; ms < MS; ++ms) {
+        mbar_init(&s.tmem_full_ms[i][ms], 1);
+        mbar_init(&s.tmem_empty[i][ms], 4 * a.epi_sets);
+      }
     }
     fence_mbar_init();
   }
@@ -562,8 +568,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || (!FUSED && a.dual && warp == 2 + 4 * a.epi_sets)) {
+    // ===================== MMA issuer(s) =====================
+    // One thread issues every MMA of an item -- or, `dual` (MS == 2), one thread per sub-tile: the two walk the same
+    // operand stages on their own (both commit to the "empty" barriers), so the thread whose accumulator is still
+    // being drained falls a few weight tiles behind while the other keeps the tensor pipe busy -- with a single
+    // accumulator stage (N > 128) both sub-tiles of an item used to finish together and the pipe idled for the
+    // whole drain (profiles/README.md, round 2: 22 % of the issuing thread's time in layer 6) -- and the
+    // instruction stream between two MMAs (~16 SASS instructions on one thread) is shared by two threads.
+    const int ms_lo = (!FUSED && a.dual) ? (warp == 1 ? 0 : 1) : 0;
+    const int ms_hi = (!FUSED && a.dual) ? ms_lo + 1 : MS;
     if (lane == 0) {
       if (RESIDENT) {
         mbar_wait(&s.w_full, 0);
@@ -602,6 +616,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const uint64_t db = sw_desc<K32>(b_addr);
 #pragma unroll
               for (int ms = 0; ms < MS; ++ms) {
+                if (ms < ms_lo || ms >= ms_hi) continue;      // (the other issuer's sub-tile)
                 if (kb == 0 && tap == 0 && wp == 0) {   // first touch of this accumulator: wait until drained
                   mbar_wait(&s.tmem_empty[stage][ms], acc_phase ^ 1);
                   tc_fence_after();
@@ -637,7 +652,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             pa ^= 1;
           }
         }
-        umma_commit(&s.tmem_full[stage]);
+#pragma unroll
+        for (int ms = 0; ms < MS; ++ms)
+          if (ms >= ms_lo && ms < ms_hi) umma_commit(&s.tmem_full_ms[stage][ms]);
         if (++stage == a.acc_stages) {
           stage = 0;
           acc_phase ^= 1;
@@ -774,12 +791,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                  : static_cast<int64_t>(b) * a.Lp_out + tp;
         }
       }
-      mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
-      tc_fence_after();
       // work units = (sub-tile, 16-column chunk), dealt round-robin to the epilogue sets
       int u = eset;
 #pragma unroll
       for (int ms = 0; ms < MS; ++ms) {
+        mbar_wait_relaxed(&s.tmem_full_ms[stage][ms], acc_phase);      // this sub-tile's accumulator is complete
+        tc_fence_after();
         void* orow = a.out_fp32
                          ? static_cast<void*>(static_cast<float*>(a.out) + out_row[ms] * row_elems + n0)
                          : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
@@ -2398,6 +2415,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fixed + static_cast<size_t>(a.a_stages) * a_group + static_cast<size_t>(a.b_stages) * b_bytes;
     }
     a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+    a.dual = (a.ms == 2 && !a.resident && env_int("RISER_DUAL_ISSUE", 1)) ? 1 : 0;
     // four epilogue sets when there are enough 16-column chunks to split (the fused kernel keeps
     // two: its thread budget goes to the layer-0 converter warps)
     a.epi_sets = (i == 1 && p->fuse_l0) ? 2 : std::max(2, std::min(env_int("RISER_EPI_SETS", kMaxEpiSets), 4));
@@ -2594,7 +2612,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
     RISER_CUDA_TRY(cudaGetLastError());
     return RISER_OK;
   }
-  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32, a.f8)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets, lp.smem, st>>>(lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, a);
+  pick_conv_kernel(a.ms, a.planes, a.wplanes, a.resident, fused, a.k32, a.f8)<<<grid, fused ? kConvThreads + kCvtThreads : 64 + 128 * a.epi_sets + (a.dual ? 32 : 0), lp.smem, st>>>(lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, a);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

@@ -157,6 +157,65 @@ maxpool_cl_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_
   }
 }
 
+// The stem in one pass (resnet.py:79-84): Conv1d(1 -> C, K, stride, padding) + folded BatchNorm + ReLU followed by
+// MaxPool1d(2, 2, padding 1) -- the convolution's output (the largest activation of the net) never goes to memory.
+// A CTA takes kStemTile pooled positions of one read: the signal span they need is staged in shared memory
+// (zeros outside [0, len_in)), a thread computes 4 channels of one pooled position = 2 conv positions x K taps.
+constexpr int kStemTile = 128, kStemThreads = 256, kStemMaxK = 32;
+__global__ void __launch_bounds__(kStemThreads)
+stem_pool_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ len_in, const float* __restrict__ w,
+                 const float* __restrict__ bias, float* __restrict__ out, const int32_t* __restrict__ len_conv,
+                 const int32_t* __restrict__ len_out, int B, int Lout_pad, int Cp, int K, int stride, int pad,
+                 int tiles_per_read) {
+  extern __shared__ __align__(16) float stem_smem[];
+  float* ws = stem_smem;                        // [K][Cp]
+  float* bs = ws + K * Cp;                      // [Cp]
+  float* xs = bs + Cp;                          // signal span of the tile
+  for (int i = threadIdx.x; i < K * Cp; i += kStemThreads) ws[i] = w[i];
+  for (int i = threadIdx.x; i < Cp; i += kStemThreads) bs[i] = bias[i];
+  const int span = (2 * kStemTile - 1) * stride + K;
+  const int G = Cp >> 2;
+  for (int item = blockIdx.x; item < B * tiles_per_read; item += gridDim.x) {
+    const int b = item / tiles_per_read;
+    const int j0 = (item - b * tiles_per_read) * kStemTile;
+    const int n_out = len_out[b];
+    if (j0 >= n_out) continue;
+    const int n_in = len_in[b], n_conv = len_conv[b];
+    const int x0 = (2 * j0 - 1) * stride - pad;            // signal index of xs[0]
+    __syncthreads();                                       // (weights staged / previous tile done with xs)
+    const float* xb = x + static_cast<int64_t>(b) * ld_x;
+    for (int i = threadIdx.x; i < span; i += kStemThreads) {
+      const int t = x0 + i;
+      xs[i] = (t >= 0 && t < n_in) ? __ldg(xb + t) : 0.f;
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < kStemTile * G; u += kStemThreads) {
+      const int jl = u / G, c = (u - jl * G) << 2;
+      const int j = j0 + jl;
+      if (j >= n_out) continue;
+      const float4 bb = *reinterpret_cast<const float4*>(bs + c);
+      float a0[4] = {bb.x, bb.y, bb.z, bb.w}, a1[4] = {bb.x, bb.y, bb.z, bb.w};
+      const float* xp = xs + 2 * jl * stride;              // conv position 2j - 1 starts here, 2j `stride` further
+      for (int k = 0; k < K; ++k) {
+        const float4 wk = *reinterpret_cast<const float4*>(ws + k * Cp + c);
+        const float v0 = xp[k], v1 = xp[k + stride];
+        a0[0] = fmaf(wk.x, v0, a0[0]); a0[1] = fmaf(wk.y, v0, a0[1]); a0[2] = fmaf(wk.z, v0, a0[2]); a0[3] = fmaf(wk.w, v0, a0[3]);
+        a1[0] = fmaf(wk.x, v1, a1[0]); a1[1] = fmaf(wk.y, v1, a1[1]); a1[2] = fmaf(wk.z, v1, a1[2]); a1[3] = fmaf(wk.w, v1, a1[3]);
+      }
+      const bool ok0 = (2 * j - 1 >= 0) && (2 * j - 1 < n_conv), ok1 = 2 * j < n_conv;     // -inf padding of the pool
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float m = -INFINITY;
+        if (ok0) m = fmaxf(a0[e], 0.f);
+        if (ok1) m = fmaxf(m, fmaxf(a1[e], 0.f));
+        r[e] = m;
+      }
+      *reinterpret_cast<float4*>(out + (static_cast<int64_t>(b) * Lout_pad + j) * Cp + c) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
 // AdaptiveAvgPool1d(1) + Flatten + Linear(C, n_classes) + softmax (resnet.py:94-98, model.py:27)
 __global__ void __launch_bounds__(128)
 gap_linear_softmax_kernel(const float* __restrict__ in, const int32_t* __restrict__ len, const float* __restrict__ fc_w,
@@ -278,6 +337,22 @@ extern "C" int riser_maxpool1d_cl(const float* in, const int32_t* len_in, float*
   RISER_REQUIRE(in && len_in && out && len_out, "riser_maxpool1d_cl: null pointer");
   const int64_t total = static_cast<int64_t>(B) * Lout_pad * C;
   maxpool_cl_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(in, len_in, out, len_out, B, Lin_pad, Lout_pad, C);
+  RISER_CUDA_TRY(cudaGetLastError());
+  return RISER_OK;
+}
+
+extern "C" int riser_stem_pool_cl(const float* x, int64_t ld_x, const int32_t* len_in, const float* w, const float* bias,
+                                  float* out, const int32_t* len_conv, const int32_t* len_out, int B, int Lout_pad,
+                                  int Cp, int K, int stride, int pad, riser_stream_t stream) {
+  RISER_REQUIRE(x && len_in && w && bias && out && len_conv && len_out, "riser_stem_pool_cl: null pointer");
+  RISER_REQUIRE(B > 0 && Lout_pad > 0 && Cp > 0 && (Cp & 3) == 0 && K > 0 && K <= kStemMaxK && stride > 0 && pad >= 0,
+                "riser_stem_pool_cl: bad shape (Cp %d multiple of 4, K %d <= %d)", Cp, K, kStemMaxK);
+  const int tiles = (Lout_pad + kStemTile - 1) / kStemTile;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(K) * Cp + Cp + (2 * kStemTile - 1) * stride + K + 4);
+  RISER_REQUIRE(smem <= 48 * 1024, "riser_stem_pool_cl: %zu bytes of shared memory", smem);
+  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(B) * tiles, 148 * 8));
+  stem_pool_kernel<<<grid, kStemThreads, smem, as_stream(stream)>>>(x, ld_x, len_in, w, bias, out, len_conv, len_out, B,
+                                                                     Lout_pad, Cp, K, stride, pad, tiles);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
 }

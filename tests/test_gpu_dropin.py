@@ -104,9 +104,11 @@ def test_mad_normalise_input_dtypes():
     x16[0] = 1500
     x16[-1] = -900
     want = pp.mad_normalise(x16).astype(np.float32)
-    for dt in (np.int16, np.int32, np.int64, np.uint16, np.float64):
+    for dt in (np.int16, np.int32, np.int64, np.float64):
         got = proc.mad_normalise(x16.astype(dt))
         assert got.dtype == np.float64 and np.array_equal(got.astype(np.float32), want), dt
+    got = proc.mad_normalise(np.abs(x16).astype(np.uint16))
+    assert np.array_equal(got.astype(np.float32), pp.mad_normalise(np.abs(x16)).astype(np.float32))
     # float32: numpy keeps float32 for the median, the MAD, the division and the smoothing
     for xf in (x16.astype(np.float32), (x16 * 0.1759 + 3.2).astype(np.float32)):
         got = proc.mad_normalise(xf)

@@ -1,9 +1,7 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2a_tests.log
-python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_st256.json 2> gpurun_out/r2a_bench_st256.err
-RISER_B200_LIB=build_ab/st128.so python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_st128.json 2> gpurun_out/r2a_bench_st128.err
-python bench.py --no-cpu-baseline > gpurun_out/r2a_bench_st256b.json 2>> gpurun_out/r2a_bench_st256.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2a_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-RISER_B200_LIB=build_ab/st128.so ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2a_launches_st128.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"fused01|conv_tc|conv_eo" -s 11 -c 11 -o gpurun_out/r2a_conv_full -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2> gpurun_out/r2a_ncu.err
-tail -3 gpurun_out/r2a_tests.log; cat gpurun_out/r2a_bench_st256.json gpurun_out/r2a_bench_st128.json gpurun_out/r2a_bench_st256b.json | cut -c1-400
+timeout 600 python -m pytest tests/test_gpu_resnet.py -m gpu -q -s 2>&1 | tail -15 > gpurun_out/r2f_resnet_tests.log
+timeout 120 python tools/debug_resnet_tc.py basic > gpurun_out/r2f_dbg_basic.log 2>&1
+for cfg in basic bottleneck; do for tc in 1 0; do RISER_RESNET_TC=$tc timeout 120 python tools/time_resnet.py 512 12048 $cfg >> gpurun_out/r2f_time_resnet.log 2>&1; done; done
+timeout 120 python tools/time_resnet.py 4096 12048 basic >> gpurun_out/r2f_time_resnet.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2f_resnet_launches.csv python tools/time_resnet.py 512 12048 basic > /dev/null 2>&1
+cat gpurun_out/r2f_resnet_tests.log gpurun_out/r2f_dbg_basic.log gpurun_out/r2f_time_resnet.log
