@@ -37,6 +37,11 @@ namespace {
 #ifndef RISER_DBG
 #define RISER_DBG 0
 #endif
+// 1: the MMA-issuing loops are run by the whole warp with the instruction predicated on the elected lane (A/B timing
+// builds: 0 = the loop under `if (lane == 0)`)
+#ifndef RISER_UNIFORM_ISSUE
+#define RISER_UNIFORM_ISSUE 1
+#endif
 constexpr int kMaxLayers = 16;
 constexpr int kBlockM = 128;          // rows per tile (UMMA M)
 constexpr int kBlockK = 64;           // fp16 elements per K block = 128 bytes = one swizzle row
@@ -464,7 +469,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                                          : static_cast<size_t>(a.b_stages) * b_bytes;
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + b_region_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int n_items = a.n_supers * a.n_tiles;
 
@@ -578,7 +583,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // instruction stream between two MMAs (~16 SASS instructions on one thread) is shared by two threads.
     const int ms_lo = (!FUSED && a.dual) ? (warp == 1 ? 0 : 1) : 0;
     const int ms_hi = (!FUSED && a.dual) ? ms_lo + 1 : MS;
-    if (lane == 0) {
+    // the whole warp runs the loop (uniform registers); only the elected lane executes the MMAs / commits
+    const uint32_t leader = (RISER_UNIFORM_ISSUE ? elect_one() : (lane == 0)) ? 1u : 0u;
+    if (RISER_UNIFORM_ISSUE || lane == 0) {
       if (RESIDENT) {
         mbar_wait(&s.w_full, 0);
         tc_fence_after();
@@ -626,19 +633,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                   const uint64_t da =
                       FUSED ? sw_desc<K32>(a_addr + ap * kFusedTileBytes + (ms * kBlockM + tap) * kRowBytes)
                             : sw_desc<K32>(a_addr + (ms * PLANES + ap) * kATile + tap * kRowBytes);
+                  if (leader) {      // one elected lane issues; the K steps of a view in one go
 #pragma unroll
-                  for (int k = 0; k < kKElems / 16; ++k)
-                    if (k < nk && !((RISER_DBG & 64) && (kb | tap | wp | ap | k) != 0)) {
-                      if (is8)
-                        umma_f8(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
-                      else
-                        umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
-                                 (kb | tap | wp | ap | k) != 0);
-                    }
+                    for (int k = 0; k < kKElems / 16; ++k)
+                      if (k < nk && !((RISER_DBG & 64) && (kb | tap | wp | ap | k) != 0)) {
+                        if (is8)
+                          umma_f8(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
+                        else
+                          umma_f16(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc,
+                                   (kb | tap | wp | ap | k) != 0);
+                      }
+                  }
                 }
               }
               if (!RESIDENT) {
-                umma_commit(&s.b_empty[sb]);
+                umma_commit_p(leader, &s.b_empty[sb]);
                 if (++sb == a.b_stages) {
                   sb = 0;
                   pb ^= 1;
@@ -646,7 +655,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               }
             }
           }
-          umma_commit(&s.a_empty[sa]);
+          umma_commit_p(leader, &s.a_empty[sa]);
           if (++sa == a.a_stages) {
             sa = 0;
             pa ^= 1;
@@ -654,7 +663,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         }
 #pragma unroll
         for (int ms = 0; ms < MS; ++ms)
-          if (ms >= ms_lo && ms < ms_hi) umma_commit(&s.tmem_full_ms[stage][ms]);
+          if (ms >= ms_lo && ms < ms_hi) umma_commit_p(leader, &s.tmem_full_ms[stage][ms]);
         if (++stage == a.acc_stages) {
           stage = 0;
           acc_phase ^= 1;
@@ -969,7 +978,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
   unsigned char* x_ring = a1_ring + 2 * kA1Stage;         // signal segments, kF2XStages stages
   F2Smem& s = *reinterpret_cast<F2Smem*>(x_ring + kF2XStages * kF2XStage);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int n_items = a.n_supers;
   const int n_pairs = a.rows_in >> 1;
@@ -1090,7 +1099,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // (the whole warp runs the loop so that the descriptor arithmetic stays in uniform registers; the elected lane issues)
+    const bool leader = RISER_UNIFORM_ISSUE ? elect_one() : (lane == 0);
+    if (RISER_UNIFORM_ISSUE || lane == 0) {
       mbar_wait(&s.w_full, 0);
       tc_fence_after();
       const uint32_t w1_addr = smem_u32(w1), b0_addr = smem_u32(b0);
@@ -1108,13 +1119,15 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&s.d0_empty[h], (k0 & 1) ^ 1);
           tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
-            umma_f16(tmem_base + kF2D0Col + (h * 2 + sub) * kF2N0,
-                     sw_desc<true>(a0_addr + st * kF2A0Tile + sub * 128 * 64) + 2 * h, db0, idesc0, 0);
-          umma_commit(&s.d0_full[h]);
+            for (int sub = 0; sub < 2; ++sub)
+              umma_f16(tmem_base + kF2D0Col + (h * 2 + sub) * kF2N0,
+                       sw_desc<true>(a0_addr + st * kF2A0Tile + sub * 128 * 64) + 2 * h, db0, idesc0, 0);
+          }
+          umma_commit_p(leader, &s.d0_full[h]);
         }
-        umma_commit(&s.a0_empty[st]);
+        umma_commit_p(leader, &s.a0_empty[st]);
         ++k0;
       };
       int cur = iter.take();
@@ -1137,6 +1150,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         // Consecutive MMAs go to DIFFERENT accumulators (sub-tile x parity, round-robin): back-to-back
         // MMAs into the same TMEM tile serialise on the accumulator (~80 cycles each at N = 32).
         auto issue_group = [&](uint32_t a_tiles, uint32_t w_set, bool f8, bool first) {
+          if (!leader) return;
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
 #pragma unroll
@@ -1165,8 +1179,8 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
             issue_group(a1s + ap * 2 * kF2A1Tile, w1_addr + wp * 3 * 2048, false, wp == 0 && ap == 0);
         if (F8)   // correction pass: [a8 | lo8] x [W_lo | W_hi * 2^-9], 64 e4m3 per row = 2 k-steps
           issue_group(a1s + 2 * kF2A1Tile, w1_addr + 3 * 2048, true, false);
-        umma_commit(&s.a1_empty[st]);
-        umma_commit(&s.d1_full[st]);
+        umma_commit_p(leader, &s.a1_empty[st]);
+        umma_commit_p(leader, &s.d1_full[st]);
         ++k1;
         cur = nxt;
       }
@@ -1469,7 +1483,7 @@ conv_eo_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__
   const size_t b_region_bytes = static_cast<size_t>(WPLANES) * a.k_blocks * 3 * b_bytes;
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + b_region_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int n_items = a.n_supers;
   const int acc2 = a.acc_cols;                 // TMEM columns of one sub-tile: [even n | odd n], rounded to 32
@@ -1540,7 +1554,9 @@ conv_eo_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // (the whole warp runs the loop so that the descriptor arithmetic stays in uniform registers; the elected lane issues)
+    const bool leader = RISER_UNIFORM_ISSUE ? elect_one() : (lane == 0);
+    if (RISER_UNIFORM_ISSUE || lane == 0) {
       mbar_wait(&s.w_full, 0);
       tc_fence_after();
       int sa = 0, stage = 0;
@@ -1572,27 +1588,29 @@ conv_eo_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__
 #pragma unroll
               for (int ap = 0; ap < (wp == 0 ? PLANES : 1); ++ap) {      // W_lo only meets the hi plane
                 const uint32_t e_rows = a_addr + (ms * PLANES + ap) * 2 * kEoTile, o_rows = e_rows + kEoTile;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  if (k < nk) {
-                    const uint64_t w21 = sw_desc<true>(w_set) + 2 * k;
-                    const uint64_t w10 = sw_desc<true>(w_set + b_bytes) + 2 * k;
-                    const uint64_t w0 = sw_desc<true>(w_set + 2 * b_bytes) + 2 * k;
-                    umma_f16(d_even, sw_desc<true>(e_rows) + 2 * k, w10, idesc2, (kb | wp | ap | k) != 0);   // E[j]
-                    umma_f16(d_even, sw_desc<true>(o_rows + 64) + 2 * k, w21, idesc2, 1);                    // O[j]
-                    umma_f16(d_even, sw_desc<true>(o_rows) + 2 * k, w0, idesc1, 1);                          // O[j-1]
-                    umma_f16(d_odd, sw_desc<true>(e_rows + 64) + 2 * k, w21, idesc1, 1);                     // E[j+1] x w2
-                  }
+                  for (int k = 0; k < 2; ++k)
+                    if (k < nk) {
+                      const uint64_t w21 = sw_desc<true>(w_set) + 2 * k;
+                      const uint64_t w10 = sw_desc<true>(w_set + b_bytes) + 2 * k;
+                      const uint64_t w0 = sw_desc<true>(w_set + 2 * b_bytes) + 2 * k;
+                      umma_f16(d_even, sw_desc<true>(e_rows) + 2 * k, w10, idesc2, (kb | wp | ap | k) != 0);   // E[j]
+                      umma_f16(d_even, sw_desc<true>(o_rows + 64) + 2 * k, w21, idesc2, 1);                    // O[j]
+                      umma_f16(d_even, sw_desc<true>(o_rows) + 2 * k, w0, idesc1, 1);                          // O[j-1]
+                      umma_f16(d_odd, sw_desc<true>(e_rows + 64) + 2 * k, w21, idesc1, 1);                     // E[j+1] x w2
+                    }
+                }
               }
             }
           }
-          umma_commit(&s.a_empty[sa]);
+          umma_commit_p(leader, &s.a_empty[sa]);
           if (++sa == a.a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-        umma_commit(&s.tmem_full[stage]);
+        umma_commit_p(leader, &s.tmem_full[stage]);
         if (++stage == a.acc_stages) {
           stage = 0;
           acc_phase ^= 1;

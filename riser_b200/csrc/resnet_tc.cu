@@ -21,7 +21,7 @@
 // [B][L][Cp] (Cp = channels padded to 8) with per-read valid lengths, as in csrc/resnet.cu, so the stem, the
 // stem max-pool and the head kernels are shared with the CUDA-core path.
 //
-// A CTA is four warps working through the phases of an item together (convert input -> MMA -> mid-epilogue -> MMA ->
+// A CTA is eight warps working through the phases of an item together (convert input -> MMA -> mid-epilogue -> MMA ->
 // epilogue); overlap comes from several CTAs per SM and from the input of the NEXT item, which one elected thread
 // pulls into a raw fp32 staging ring with a 1-D bulk copy (the rows an item needs are contiguous in memory) while the
 // current item is worked on.  An identity shortcut is read back from that staging buffer.  Weights are copied into
@@ -38,7 +38,7 @@
 namespace riser {
 namespace {
 
-constexpr int kRtThreads = 128;
+constexpr int kRtThreads = 256;      // two warps per TMEM lane quadrant: they split the 16-column chunks of the epilogues
 constexpr uint32_t kRtTile = 136 * 64;      // one staged tile: up to 130 rows (+ slack) of 64 bytes = 32 fp16 channels
 
 struct ResTcArgs {
@@ -61,18 +61,30 @@ struct ResTcArgs {
   int relu;                      // single conv mode: ReLU in the epilogue
   int tile_rows;                 // output rows per item: 128 (single) or 126 (fused)
   int tiles_per_read, n_items;
+  uint32_t tiles_magic;          // floor(2^32 / tiles_per_read) + 1: item / tiles_per_read = umulhi(item, magic) (n_items < 2^20)
   int d2_col;                    // TMEM column of conv2's accumulator
   int tmem_cols;                 // columns allocated (power of two >= 32)
   int cat1, cat2;                // conv1 / conv2: [W_hi; W_lo] stacked (accumulator = 2 n columns, two MMAs per step)
   int raw_stages;                // raw fp32 input staging buffers (1 or 2)
   int raw_rows;                  // input rows an item stages
   uint32_t raw_bytes;            // bytes of one staging buffer
+  int n_mma1, n_mma2;            // MMAs of conv1 / conv2 (+ shortcut conv): sizes of the replay lists
 };
 
 struct RtSmem {
   uint64_t bar;
   uint64_t raw_full[2];
+  uint64_t w_full;
   uint32_t tmem_base;
+};
+
+// One MMA of an item: the operand descriptors never change from item to item (same shared-memory tiles), so the
+// issuing thread builds the list once and replays it -- two 16-byte loads and the instruction per MMA instead of
+// the loop nest with its descriptor arithmetic (a single thread issues them all: its instruction count is what
+// paces these short MMAs).
+struct alignas(16) RtMma {
+  uint64_t da, db;
+  uint32_t idesc, d_col, acc, pad_;
 };
 
 // fp32 x 8 -> fp16 hi (8 halfs = one 16-byte chunk) and lo = fp16(v - hi)
@@ -102,26 +114,84 @@ __device__ __forceinline__ uint32_t w_tile(uint32_t base, int tap, int kb, int n
 }
 
 // The MMAs of one term  D += A(view) * W(tap)  over the K blocks:  a_hi x [W_hi; W_lo] + a_lo x W_hi  (cat), or the three
-// products one by one.  a_hi / a_lo: shared-memory addresses of the hi / lo A tiles of K block 0 (consecutive K blocks
-// kRtTile apart), already shifted to the view's first row.
-__device__ __forceinline__ void issue_term(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_base, int tap, int n_kb,
-                                           int k_ch, int n, bool cat, uint32_t idesc_n, uint32_t idesc_2n, bool& first) {
+// products one by one, appended to a replay list.  a_hi / a_lo: shared-memory addresses of the hi / lo A tiles of K
+// block 0 (consecutive K blocks kRtTile apart), already shifted to the view's first row.
+__device__ __forceinline__ int list_term(RtMma* list, int n_list, uint32_t d_col, uint32_t a_hi, uint32_t a_lo,
+                                         uint32_t w_base, int tap, int n_kb, int k_ch, int n, bool cat,
+                                         uint32_t idesc_n, uint32_t idesc_2n) {
   for (int kb = 0; kb < n_kb; ++kb) {
     const int nk = min(2, (k_ch - 32 * kb + 15) >> 4);
     const uint32_t wt = w_tile(w_base, tap, kb, n_kb, n);
     for (int k = 0; k < nk; ++k) {
       const uint64_t ah = rt_desc(a_hi + kb * kRtTile) + 2 * k, al = rt_desc(a_lo + kb * kRtTile) + 2 * k;
       const uint64_t wh = rt_desc(wt) + 2 * k, wl = rt_desc(wt + n * 64) + 2 * k;
+      const uint32_t acc = n_list ? 1u : 0u;
       if (cat) {
-        umma_f16(d, ah, wh, idesc_2n, first ? 0u : 1u);        // columns [0, n): a_hi W_hi, [n, 2n): a_hi W_lo
-        umma_f16(d, al, wh, idesc_n, 1u);                      // columns [0, n) += a_lo W_hi
+        list[n_list++] = RtMma{ah, wh, idesc_2n, d_col, acc, 0u};   // columns [0, n): a_hi W_hi, [n, 2n): a_hi W_lo
+        list[n_list++] = RtMma{al, wh, idesc_n, d_col, 1u, 0u};     // columns [0, n) += a_lo W_hi
       } else {
-        umma_f16(d, ah, wh, idesc_n, first ? 0u : 1u);
-        umma_f16(d, al, wh, idesc_n, 1u);
-        umma_f16(d, ah, wl, idesc_n, 1u);
+        list[n_list++] = RtMma{ah, wh, idesc_n, d_col, acc, 0u};
+        list[n_list++] = RtMma{al, wh, idesc_n, d_col, 1u, 0u};
+        list[n_list++] = RtMma{ah, wl, idesc_n, d_col, 1u, 0u};
       }
-      first = false;
     }
+  }
+  return n_list;
+}
+
+// The same MMAs issued from a warp-uniform loop nest (the whole warp runs it, the descriptor arithmetic stays in uniform
+// registers, the elected lane executes the instructions): no shared-memory list, no R2UR per operand.
+#ifndef RISER_RT_REPLAY
+#define RISER_RT_REPLAY 1      // measured: the replayed list 1.009 ms, the uniform loop nest 1.045 ms (512 x 12,048, basic)
+#endif
+__device__ __forceinline__ void issue_term_uniform(bool leader, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t w_base,
+                                                   int tap, int n_kb, int k_ch, int n, bool cat, uint32_t idesc_n,
+                                                   uint32_t idesc_2n, uint32_t& acc) {
+  for (int kb = 0; kb < n_kb; ++kb) {
+    const int nk = min(2, (k_ch - 32 * kb + 15) >> 4);
+    const uint32_t wt = w_tile(w_base, tap, kb, n_kb, n);
+    const uint64_t ah0 = rt_desc(a_hi + kb * kRtTile), al0 = rt_desc(a_lo + kb * kRtTile);
+    const uint64_t wh0 = rt_desc(wt), wl0 = rt_desc(wt + n * 64);
+    if (leader) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (k < nk) {
+          if (cat) {
+            umma_f16(d, ah0 + 2 * k, wh0 + 2 * k, idesc_2n, (k == 0) ? acc : 1u);
+            umma_f16(d, al0 + 2 * k, wh0 + 2 * k, idesc_n, 1u);
+          } else {
+            umma_f16(d, ah0 + 2 * k, wh0 + 2 * k, idesc_n, (k == 0) ? acc : 1u);
+            umma_f16(d, al0 + 2 * k, wh0 + 2 * k, idesc_n, 1u);
+            umma_f16(d, ah0 + 2 * k, wl0 + 2 * k, idesc_n, 1u);
+          }
+        }
+    }
+    acc = 1u;
+  }
+}
+
+__device__ __forceinline__ void replay(const RtMma* list, int n, uint32_t tmem_base) {
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const RtMma e = list[i];
+    umma_f16(tmem_base + e.d_col, e.da, e.db, e.idesc, e.acc);
+  }
+}
+
+// The CTA waits for an mbarrier phase: ONE thread polls it, the others park at the hardware barrier (256 threads
+// spinning on try_wait took an eighth of the kernel's issue slots from the co-resident CTAs that had work to do).
+#ifndef RISER_RT_CTAWAIT
+#define RISER_RT_CTAWAIT 0
+#endif
+#ifndef RISER_RT_RES_GLOBAL
+#define RISER_RT_RES_GLOBAL 0
+#endif
+__device__ __forceinline__ void cta_wait(uint64_t* bar, uint32_t parity) {
+  if (RISER_RT_CTAWAIT) {
+    if (threadIdx.x == 0) mbar_wait(bar, parity);
+    __syncthreads();
+  } else {
+    mbar_wait(bar, parity);
   }
 }
 
@@ -144,24 +214,29 @@ res_tc_kernel(const ResTcArgs a) {
   unsigned char* raws = a2s + a2_bytes;                          // raw fp32 input rows, raw_stages buffers
   float* bias1s = reinterpret_cast<float*>(raws + a.raw_stages * a.raw_bytes);
   float* bias2s = bias1s + a.n1;
-  RtSmem& s = *reinterpret_cast<RtSmem*>(bias2s + (fused ? a.n2 : 0));
+  RtMma* list1 = reinterpret_cast<RtMma*>(bias2s + (fused ? a.n2 : 0));
+  RtMma* list2 = list1 + a.n_mma1;
+  RtSmem& s = *reinterpret_cast<RtSmem*>(list2 + a.n_mma2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   if (tid == 0) {
     mbar_init(&s.bar, 1);
     mbar_init(&s.raw_full[0], 1);
     mbar_init(&s.raw_full[1], 1);
+    mbar_init(&s.w_full, 1);
     fence_mbar_init();
+    // weights (already in the operand layout): bulk copies, waited for before the first MMA
+    mbar_arrive_expect_tx(&s.w_full, w1_bytes + w2_bytes + wsc_bytes);
+    bulk_load_1d(w1s, a.w1, w1_bytes, &s.w_full);
+    if (w2_bytes) bulk_load_1d(w2s, a.w2, w2_bytes, &s.w_full);
+    if (wsc_bytes) bulk_load_1d(wscs, a.wsc, wsc_bytes, &s.w_full);
   }
   if (warp == 0) {
     tmem_alloc(&s.tmem_base, a.tmem_cols);
     tmem_relinquish();
   }
-  // weights (already in the operand layout) and biases once per CTA; operand tiles zeroed once: channels beyond
-  // cin_p / cmid_p inside the last K block are never written afterwards and must not hold NaN patterns
-  for (uint32_t i = tid; i < w1_bytes / 16; i += kRtThreads) reinterpret_cast<uint4*>(w1s)[i] = a.w1[i];
-  for (uint32_t i = tid; i < w2_bytes / 16; i += kRtThreads) reinterpret_cast<uint4*>(w2s)[i] = a.w2[i];
-  for (uint32_t i = tid; i < wsc_bytes / 16; i += kRtThreads) reinterpret_cast<uint4*>(wscs)[i] = a.wsc[i];
+  // biases once per CTA; operand tiles zeroed once: channels beyond cin_p / cmid_p inside the last K block are never
+  // written afterwards and must not hold NaN patterns
   for (uint32_t i = tid; i < (a1_bytes + a2_bytes) / 16; i += kRtThreads)
     reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < a.n1; i += kRtThreads) bias1s[i] = a.bias1[i];
@@ -180,11 +255,40 @@ res_tc_kernel(const ResTcArgs a) {
   const int groups = a.cin_p >> 3;                               // 8-channel groups per input row
   const int pad = (a.taps - 1) >> 1;
   const int row_bytes = a.cin_p * 4;
+  const int step_g = kRtThreads % groups, step_r = kRtThreads / groups;
   uint32_t phase = 0;
+  if (tid == 0) {
+    // conv1: D1[128 x n1] = sum over taps / K of A1(view) * W1
+    int n = 0;
+    for (int tap = 0; tap < a.taps; ++tap) {
+      int part = 0, shift = tap;
+      if (a.stride == 2) {
+        if (a.taps == 1 || tap == 1) { part = 0; shift = 0; }           // E[m]  (w1 E[m])
+        else { part = 1; shift = (tap == 2) ? 1 : 0; }                  // w0 O[m-1], w2 O[m]
+      }
+      const uint32_t av = a1_addr + part * a.kb1 * kRtTile + shift * 64;
+      n = list_term(list1, n, 0u, av, av + a1_lo, w1_addr, tap, a.kb1, a.cin_p, a.n1, a.cat1 != 0, idesc1, idesc1c);
+    }
+    if (fused) {
+      // conv2 (+ 1x1 shortcut conv): D2[i] = sum_t W2_t A2[i + t]  (+ Wsc x[s (p0 + i)])
+      n = 0;
+      for (int tap = 0; tap < 3; ++tap) {
+        const uint32_t av = a2_addr + tap * 64;
+        n = list_term(list2, n, a.d2_col, av, av + a2_lo, w2_addr, tap, a.kb2, a.cmid_p, a.n2, a.cat2 != 0, idesc2, idesc2c);
+      }
+      if (a.wsc) {
+        // x[s (p0 + i)]: stride 1 -> X row i + 1 + pad; stride 2 -> E row i + 1
+        const uint32_t av = a1_addr + ((a.stride == 2) ? 1 : 1 + pad) * 64;
+        n = list_term(list2, n, a.d2_col, av, av + a1_lo, wsc_addr, 0, a.kb1, a.cin_p, a.n2, a.cat2 != 0, idesc2, idesc2c);
+      }
+    }
+    mbar_wait(&s.w_full, 0);                                     // the weight images have landed
+  }
+  __syncwarp();
 
   // item -> (read, first output row); an item whose rows all lie beyond its read's valid length is skipped
   auto decode = [&](int item, int& b, int& p0) {
-    b = item / a.tiles_per_read;
+    b = static_cast<int>(__umulhi(static_cast<uint32_t>(item), a.tiles_magic));     // item / tiles_per_read
     p0 = (item - b * a.tiles_per_read) * a.tile_rows;
   };
   auto next_active = [&](int item) {
@@ -228,12 +332,16 @@ res_tc_kernel(const ResTcArgs a) {
 
     // ---------------- convert: raw fp32 rows -> fp16 hi / lo tiles (swizzled K-major)
     // stride 1: X row r = x[q0 - pad + r];  stride 2: E row r = x[2 (q0 + r)], O row r = x[2 (q0 - 1 + r) + 1]
-    mbar_wait(&s.raw_full[slot], (a.raw_stages == 2) ? ((k >> 1) & 1) : (k & 1));
+    cta_wait(&s.raw_full[slot], (a.raw_stages == 2) ? ((k >> 1) & 1) : (k & 1));
     const float* raw = reinterpret_cast<const float*>(raws + slot * a.raw_bytes);
-    const int n_units = a.raw_rows * groups;
-    for (int u = tid; u < n_units; u += kRtThreads) {
-      const int g = u % groups;
-      const int rr = u / groups;                                  // raw row = input position pos0 + rr
+    // unit u = (raw row rr, 8-channel group g), u = rr * groups + g; a thread's units are kRtThreads apart
+    int g = tid % groups, rr = tid / groups;                      // raw row = input position pos0 + rr
+    for (; rr < a.raw_rows; g += step_g, rr += step_r) {
+      if (g >= groups) {
+        g -= groups;
+        ++rr;
+        if (rr >= a.raw_rows) break;
+      }
       const int pos = pos0 + rr;
       int part = 0, r = rr;
       if (a.stride == 2) {
@@ -261,13 +369,20 @@ res_tc_kernel(const ResTcArgs a) {
     tc_fence_before();
     __syncthreads();
     // one staging buffer: it is free again unless the epilogue reads the identity shortcut from it
-    const bool res_from_raw = fused && a.residual && !a.wsc && a.stride == 1;
+    const bool res_from_raw = fused && a.residual && !a.wsc && a.stride == 1 && (a.raw_stages == 2 || !RISER_RT_RES_GLOBAL);
     if (a.raw_stages == 1 && !res_from_raw && tid == 0 && nxt < a.n_items) prefetch(nxt, 0);
 
     // ---------------- conv1: D1[128 x n1] = sum over taps / K of A1(view) * W1
-    if (tid == 0) {
+    if (RISER_RT_REPLAY) {
+      if (tid == 0) {
+        tc_fence_after();
+        replay(list1, a.n_mma1, tmem_base);
+        umma_commit(&s.bar);
+      }
+    } else if (warp == 0) {
+      const bool leader = elect_one();
       tc_fence_after();
-      bool first = true;
+      uint32_t acc = 0u;
       for (int tap = 0; tap < a.taps; ++tap) {
         int part = 0, shift = tap;
         if (a.stride == 2) {
@@ -275,21 +390,23 @@ res_tc_kernel(const ResTcArgs a) {
           else { part = 1; shift = (tap == 2) ? 1 : 0; }                  // w0 O[m-1], w2 O[m]
         }
         const uint32_t av = a1_addr + part * a.kb1 * kRtTile + shift * 64;
-        issue_term(tmem_base, av, av + a1_lo, w1_addr, tap, a.kb1, a.cin_p, a.n1, a.cat1 != 0, idesc1, idesc1c, first);
+        issue_term_uniform(leader, tmem_base, av, av + a1_lo, w1_addr, tap, a.kb1, a.cin_p, a.n1, a.cat1 != 0, idesc1,
+                           idesc1c, acc);
       }
-      umma_commit(&s.bar);
+      umma_commit_p(leader ? 1u : 0u, &s.bar);
     }
-    mbar_wait(&s.bar, phase);
+    cta_wait(&s.bar, phase);
     phase ^= 1;
     tc_fence_after();
 
-    const int row = 32 * warp + lane;                              // this thread's accumulator row (TMEM lane)
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(32 * warp) << 16);
+    const int quad = warp & 3, half = warp >> 2;                   // TMEM lane quadrant; which chunks of it this warp takes
+    const int row = 32 * quad + lane;                              // this thread's accumulator row (TMEM lane)
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(32 * quad) << 16);
     if (fused) {
       // ---------------- mid-epilogue: bias + ReLU + length mask -> conv2's A operand (row j = mid row q0 + j)
       const int m = q0 + row;
       const bool live = (m >= 0 && m < n_out);
-      for (int c16 = 0; c16 < a.n1; c16 += 16) {
+      for (int c16 = 16 * half; c16 < a.n1; c16 += 32) {
         uint32_t v[16], w[16];
         tmem_ld_32x16(t_lane + c16, v);
         if (a.cat1) tmem_ld_32x16(t_lane + a.n1 + c16, w);
@@ -318,22 +435,29 @@ res_tc_kernel(const ResTcArgs a) {
       __syncthreads();
 
       // ---------------- conv2 (+ 1x1 shortcut conv): D2[i] = sum_t W2_t A2[i + t]  (+ Wsc x[s (p0 + i)])
-      if (tid == 0) {
+      if (RISER_RT_REPLAY) {
+        if (tid == 0) {
+          tc_fence_after();
+          replay(list2, a.n_mma2, tmem_base);
+          umma_commit(&s.bar);
+        }
+      } else if (warp == 0) {
+        const bool leader = elect_one();
         tc_fence_after();
-        bool first = true;
+        uint32_t acc = 0u;
         const uint32_t d2 = tmem_base + a.d2_col;
         for (int tap = 0; tap < 3; ++tap) {
           const uint32_t av = a2_addr + tap * 64;
-          issue_term(d2, av, av + a2_lo, w2_addr, tap, a.kb2, a.cmid_p, a.n2, a.cat2 != 0, idesc2, idesc2c, first);
+          issue_term_uniform(leader, d2, av, av + a2_lo, w2_addr, tap, a.kb2, a.cmid_p, a.n2, a.cat2 != 0, idesc2, idesc2c, acc);
         }
         if (a.wsc) {
           // x[s (p0 + i)]: stride 1 -> X row i + 1 + pad; stride 2 -> E row i + 1
           const uint32_t av = a1_addr + ((a.stride == 2) ? 1 : 1 + pad) * 64;
-          issue_term(d2, av, av + a1_lo, wsc_addr, 0, a.kb1, a.cin_p, a.n2, a.cat2 != 0, idesc2, idesc2c, first);
+          issue_term_uniform(leader, d2, av, av + a1_lo, wsc_addr, 0, a.kb1, a.cin_p, a.n2, a.cat2 != 0, idesc2, idesc2c, acc);
         }
-        umma_commit(&s.bar);
+        umma_commit_p(leader ? 1u : 0u, &s.bar);
       }
-      mbar_wait(&s.bar, phase);
+      cta_wait(&s.bar, phase);
       phase ^= 1;
       tc_fence_after();
     }
@@ -355,7 +479,7 @@ res_tc_kernel(const ResTcArgs a) {
       if (a.residual)
         rrow = res_from_raw ? raw + (row + 1 + pad) * a.cin_p
                             : a.residual + (static_cast<int64_t>(b) * a.Lout_pad + p) * a.cout_p;
-      for (int c16 = 0; c16 < n; c16 += 16) {
+      for (int c16 = 16 * half; c16 < n; c16 += 32) {
         uint32_t v[16], w[16];
         tmem_ld_32x16(t_acc + c16, v);
         if (cat) tmem_ld_32x16(t_acc + n + c16, w);
@@ -418,6 +542,11 @@ using namespace riser;
 namespace riser {
 namespace {
 int raw_rows_of(int taps, int stride) { return stride == 2 ? 258 : 128 + (taps - 1); }
+int mma_count(int taps, int k_ch, int n) {       // MMAs of `taps` terms over k_ch channels (two per step stacked, else three)
+  int steps = 0;
+  for (int kb = 0; kb < (k_ch + 31) / 32; ++kb) steps += std::min(2, (k_ch - 32 * kb + 15) >> 4);
+  return taps * steps * (2 * n <= 256 ? 2 : 3);
+}
 size_t raw_bytes_of(int cin_p, int taps, int stride) {
   return (static_cast<size_t>(raw_rows_of(taps, stride)) * cin_p * 4 + 127) & ~size_t(127);
 }
@@ -434,7 +563,8 @@ extern "C" size_t riser_res_tc_smem(int cin_p, int cmid_p, int n1, int n2, int t
   const int kb1 = (cin_p + 31) / 32, kb2 = fused ? (cmid_p + 31) / 32 : 0;
   const int parts = stride == 2 ? 2 : 1;
   size_t bytes = 1024 + 2u * taps * kb1 * n1 * 64u + 2u * parts * kb1 * kRtTile + raw_bytes_of(cin_p, taps, stride) +
-                 sizeof(float) * n1 + sizeof(RtSmem) + 64;
+                 sizeof(float) * n1 + sizeof(RtSmem) + 64 +
+                 sizeof(RtMma) * (mma_count(taps, cin_p, n1) + (fused ? mma_count(3, cmid_p, n2) + (shortcut_conv ? mma_count(1, cin_p, n2) : 0) : 0));
   if (fused) {
     bytes += 2u * 3 * kb2 * n2 * 64u + 2u * kb2 * kRtTile + sizeof(float) * n2;
     if (shortcut_conv) bytes += ((2u * kb1 * n2 * 64u) + 511u) & ~size_t(511);
@@ -480,10 +610,14 @@ extern "C" int riser_res_tc(const float* in, const int32_t* len_in, const int32_
   a.tile_rows = fused ? 126 : 128;
   a.tiles_per_read = (Lout_pad + a.tile_rows - 1) / a.tile_rows;
   a.n_items = B * a.tiles_per_read;
+  RISER_REQUIRE(a.n_items < (1 << 20), "riser_res_tc: %d work items (B x tiles per read) exceed 2^20", a.n_items);
+  a.tiles_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(a.tiles_per_read)) + 1u;
   a.cat1 = (2 * n1 <= 256) ? 1 : 0;
   a.cat2 = (fused && 2 * n2 <= 256) ? 1 : 0;
   a.d2_col = ((a.cat1 ? 2 * n1 : n1) + 31) & ~31;
   a.tmem_cols = pow2_at_least(a.d2_col + (fused ? (((a.cat2 ? 2 * n2 : n2) + 31) & ~31) : 0));
+  a.n_mma1 = mma_count(taps, cin_p, n1);
+  a.n_mma2 = fused ? mma_count(3, cmid_p, n2) + (wsc ? mma_count(1, cin_p, n2) : 0) : 0;
   a.raw_rows = raw_rows_of(taps, stride);
   a.raw_bytes = static_cast<uint32_t>(raw_bytes_of(cin_p, taps, stride));
   // CTAs per SM: as many as shared memory allows, but their TMEM allocations must fit the 512 columns of an SM

@@ -1,7 +1,7 @@
 """Where do the single-thread roles of a conv kernel wait?  For one captured launch (ncu --set full --import-source on)
 list the mbarrier try-wait spin loops (SYNCS.PHASECHK...TRYWAIT + the branch behind it) by barrier -- the offset in
 ConvSmem names the barrier: a_full 0x00, a_empty 0x40, b_full 0x80, b_empty 0xc0, w_full 0x100, tmem_full 0x108,
-tmem_empty 0x128.. -- with their stall samples, next to the kernel's headline counters.
+tmem_full_ms 0x128 (conv_tc_kernel: per stage and sub-tile), tmem_empty 0x1a8.. -- with their stall samples, next to the kernel's headline counters.
 
     python tools/ncu_waits.py report.ncu-rep <launch index>
 """
@@ -12,8 +12,8 @@ import subprocess
 import sys
 
 rep, idx = sys.argv[1], sys.argv[2]
-NAMES = [(0x128, "tmem_empty"), (0x108, "tmem_full"), (0x100, "w_full"), (0xc0, "b_empty"), (0x80, "b_full"),
-         (0x40, "a_empty"), (0x00, "a_full")]
+NAMES = [(0x1a8, "tmem_empty"), (0x128, "tmem_full_ms"), (0x108, "tmem_full"), (0x100, "w_full"), (0xc0, "b_empty"),
+         (0x80, "b_full"), (0x40, "a_empty"), (0x00, "a_full")]
 
 
 def barrier(off):
