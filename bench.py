@@ -97,11 +97,11 @@ def burst_peak():
     return 1590.0
 
 
-def pass_equivalents(length, precision, f8_from):
+def pass_equivalents(length, precision, formats):
     """fp16-pass-equivalents of tensor work executed per algorithmic FLOP of the conv stack (FLOP-weighted over
-    layers 1..11): F16 1, F16_W2 2, F16_X3 3; F16_F8: 3 in layers < f8_from (hi + lo planes), 2 from there on
-    (fp16 pass + one e4m3 pass of twice the K at twice the rate).  1 / this = the structural ceiling of
-    roofline.frac at a perfect tensor pipe."""
+    layers 1..11): F16 1, F16_W2 2, F16_X3 3; F16_F8: per layer by the row format the plan reports for its input
+    (riser_plan_layer_format) -- 3 for hi + lo fp16 planes, 2 for the e4m3 format (fp16 pass + one e4m3 pass of
+    twice the K at twice the rate).  1 / this = the structural ceiling of roofline.frac at a perfect tensor pipe."""
     if precision != 3:
         return {0: 1.0, 1: 2.0, 2: 3.0}[precision]
     tot = w = 0.0
@@ -110,7 +110,7 @@ def pass_equivalents(length, precision, f8_from):
         f = 2 * 3 * cin * c * l
         if i >= 1:
             tot += f
-            w += f * (2.0 if i >= f8_from else 3.0)
+            w += f * {1: 2.0, 2: 3.0, 3: 2.0}[formats[i]]
         cin, l = c, l // 2
     return w / tot
 
@@ -645,8 +645,15 @@ def main():
             with open(tpath) as f:
                 traffic = json.load(f).get(f"B{B}_L{L}_p{precision}")
         launches_per_step = 1 + mdl.launches(B, L, clf.chunk) + 1
-        f8_from = int(os.environ.get("RISER_F8_FROM", "6"))
-        peq = pass_equivalents(L, precision, f8_from)
+        plan = mdl.plan(B, L)
+        formats = {i: plan.layer_format(i) for i in range(1, len(CHANNELS))}
+        peq = pass_equivalents(L, precision, formats)
+        kern = {}
+        for i in range(1, len(CHANNELS)):
+            kern.setdefault(plan.layer_kernel(i), []).append(i)
+        kern_desc = " + ".join(f"{k} (layer{'s' if len(v) > 1 else ''} {'0+' if k.startswith('fused01') else ''}"
+                               f"{','.join(map(str, v))})" for k, v in kern.items())
+        f8_layers = [i for i, f in formats.items() if f == 3]
         tsrc = None
         if os.path.exists(tpath):
             with open(tpath) as f:
@@ -662,11 +669,11 @@ def main():
                     "arithmetic": {0: "f16 operands, f32 accumulate (1 tcgen05 pass)",
                                    1: "f16, weights split hi+lo (2 passes), f32 accumulate",
                                    2: "f16, weights and activations split hi+lo (3 passes), f32 accumulate",
-                                   3: "f16 pass + e4m3 correction pass carrying the hi/lo terms (2 pass-equivalents; "
-                                      "layers 1-5 as mode 2), f32 accumulate; layer 0 and the head in f32, "
-                                      "normalise in f64"}[precision],
+                                   3: "f16 pass + e4m3 correction pass carrying the hi/lo terms (2 pass-equivalents) in "
+                                      f"layers {f8_layers[0] if f8_layers else '-'}-11, the other conv layers as mode 2; "
+                                      "f32 accumulate; layer 0 and the head in f32, normalise in f64"}[precision],
                     "chunk": clf.chunk, "decisions_made": n_dec},
-            "roofline": {"bound": "tensor", "kernel": "fused01_kernel + conv_eo_kernel x3 + conv_tc_kernel x7 (layers %d-11, 11 launches per forward)" % (0 if fused else 1),
+            "roofline": {"bound": "tensor", "kernel": kern_desc + " -- %d launches per forward" % (len(CHANNELS) - (1 if fused else 0)),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "traffic_source": tsrc, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "frac_burst": achieved / burst_peak(), "peak_burst": burst_peak(),

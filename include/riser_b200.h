@@ -184,7 +184,9 @@ int riser_forward(const riser_plan* p, const float* x, int64_t ld_x, const int32
  * events between them (bench.py times the conv stack):
  *   0 = tile activity flags (+ layer 0 when it is not fused into layer 1's launch);
  *   1 = the conv layers (tcgen05; layers 0 + 1 are one launch by default);  2 = head;
- *   3 = the layer-0 launches of stage 0 alone (timing aid, not part of riser_forward). */
+ *   3 = the layer-0 launches of stage 0 alone (timing aid, not part of riser_forward);
+ *   16 + i = conv layer i (>= 1) alone, so that a tool can bracket every layer of a forward with
+ *   CUDA events (stage 0, then 16 + 1 .. 16 + n_layers - 1, then 2 == riser_forward).          */
 int riser_forward_stage(const riser_plan* p, int stage, const float* x, int64_t ld_x,
                         const int32_t* len, float* probs, float* feat, riser_stream_t stream);
 
@@ -207,6 +209,22 @@ int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows
  * read (row = b * rows_per_read / 2 + t / 2) followed by all odd rows, instead of the flat
  * [B * rows_per_read] order.  Same size, same row format.                            */
 int riser_plan_layer_eo(const riser_plan* p, int i);
+
+/* Row format of layer i's input buffer (i = 1..n_layers-1), decided per layer by the precision
+ * mode:
+ *   1 = one fp16 plane [channels_padded];
+ *   2 = fp16 hi | fp16 lo planes (a = hi + lo; the F16_X3 terms W_hi*a_hi + W_lo*a_hi + W_hi*a_lo);
+ *   3 = fp16 hi | e4m3(a) | e4m3((a - hi) * 2^9): the operands of the fp16 pass and of the single
+ *       e4m3 correction pass of RISER_PREC_F16_F8 (same bytes per row as format 2).
+ * 0 for i outside that range.  Tests decode activations with it; bench.py derives the tensor passes
+ * executed per algorithmic FLOP from it (riser/nets/cnn.py:55-64 is one fp32 pass).            */
+int riser_plan_layer_format(const riser_plan* p, int i);
+
+/* Which kernel runs conv layer i (1..n_layers-1) in this plan: 0 = conv_tc_kernel (one CTA per SM),
+ * 1 = conv_eo_kernel (even / odd planes, resident weights), 2 = conv_pair_kernel (cta_group::2 CTA
+ * pairs), 3 = fused01_kernel (layers 0 + 1 in one launch), 4 = conv_tc_kernel with the CUDA-core
+ * layer-0 converter warps.  -1 outside the range.  For bench.py's launch description.          */
+int riser_plan_layer_kernel(const riser_plan* p, int i);
 
 /* Replaces the decision rule of riser/control.py:75-82 for M models:
  * probs [M, B, 2]; len [B] = post-trim window length, 0 = read was skipped

@@ -39,6 +39,8 @@ SIGNATURES = {
     "riser_plan_fused_layer0": (c_int, [c_void_p]),
     "riser_plan_layer_info": (c_int, [c_void_p, c_int, P(c_i64), P(c_int), P(c_int), P(c_int), P(c_int)]),
     "riser_plan_layer_eo": (c_int, [c_void_p, c_int]),
+    "riser_plan_layer_format": (c_int, [c_void_p, c_int]),
+    "riser_plan_layer_kernel": (c_int, [c_void_p, c_int]),
     "riser_conv1d_cl": (c_int, [c_void_p] * 7 + [c_int] * 9 + [c_void_p]),
     "riser_stem_pool_cl": (c_int, [c_void_p, c_i64] + [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
     "riser_res_tc_smem": (c_size_t, [c_int] * 8),

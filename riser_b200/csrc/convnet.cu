@@ -133,6 +133,8 @@ struct ConvArgs {
   unsigned long long pair_magic;   // floor(2^40 / half_lp) + 1: pair index -> read index
   uint32_t idesc;
   float w_inv_scale;
+  int n_last;                // conv_pair_kernel: width of the LAST N tile (<= n_tile; the others are n_tile wide)
+  uint32_t idesc_last;
 };
 
 struct ActivityLayer {
@@ -145,6 +147,7 @@ struct ActivityArgs {
 
 struct LayerPlan {
   CUtensorMap tm_a, tm_b, tm_a8, tm_b8;   // (EO layers: tm_a = E plane, tm_a8 = O plane)
+  CUtensorMap tm_bl, tm_b8l;              // conv_pair_kernel: weight maps whose box is half of the LAST N tile
   int eo = 0;                             // input in the even / odd plane layout -> conv_eo_kernel
   int pair = 0;                           // CTA pairs (cta_group::2) -> conv_pair_kernel
   ConvArgs args;
@@ -1717,17 +1720,18 @@ template <int MS>
 __global__ void __launch_bounds__(64 + 128 * kMaxEpiSets, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_b8,
+                 const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_b8l,
                  const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr uint32_t kATile = 136 * 128;
   constexpr uint32_t kAGroup = MS * kATile;
-  const uint32_t b_bytes = (a.n_tile / 2) * 128;           // this CTA's half of a weight tile
+  const uint32_t b_bytes = (a.n_tile / 2) * 128;           // this CTA's half of a (full-width) weight tile
   unsigned char* a_ring = base;
   unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroup;
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + static_cast<size_t>(a.b_stages) * b_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -1739,6 +1743,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_a8);
     tma_prefetch_desc(&tm_b8);
+    tma_prefetch_desc(&tm_bl);
+    tma_prefetch_desc(&tm_b8l);
     for (int i = 0; i < a.a_stages; ++i) {
       mbar_init(&s.a_full[i], 1);
       mbar_init(&s.a_empty[i], 1);
@@ -1764,8 +1770,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tmem_base = s.tmem_base;
 
   // item -> (M super-tile, N tile), N fastest; the pair visits item = pair, pair + n_pairs_grid, ...
+  // (the N tile is rotated by the super-tile index: the grid stride may be a multiple of n_tiles, and the last tile
+  //  is narrower than the others -- every pair then still gets its share of both widths)
   auto item_super = [&](int item) { return a.super0 + item / a.n_tiles; };
-  auto item_n = [&](int item) { return item % a.n_tiles; };
+  auto item_n = [&](int item) { return (item % a.n_tiles + item / a.n_tiles) % a.n_tiles; };
   auto active = [&](int item) { return !a.flags || __ldg(a.flags + item_super(item)) != 0; };
 
   if (warp == 0) {
@@ -1776,7 +1784,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int item = pair; item < n_items; item += n_pairs_grid) {
         if (!active(item)) continue;
         const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM - 1;
-        const int n0 = item_n(item) * a.n_tile + static_cast<int>(rank) * (a.n_tile / 2);
+        const int n_idx = item_n(item);
+        const bool last_n = (n_idx == a.n_tiles - 1);
+        const int n_half = (last_n ? a.n_last : a.n_tile) / 2;       // weight rows this CTA stages per tile
+        const int n0 = n_idx * a.n_tile + static_cast<int>(rank) * n_half;
+        const uint32_t b_tx = static_cast<uint32_t>(n_half) * 128;
+        const CUtensorMap* tb = last_n ? &tm_bl : &tm_b;
+        const CUtensorMap* tb8 = last_n ? &tm_b8l : &tm_b8;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
           const bool is8 = kb >= a.kb16;
           mbar_wait(&s.a_empty[sa], pa ^ 1);
@@ -1796,12 +1810,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
             mbar_wait(&s.b_empty[sb], pb ^ 1);
-            if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_bytes);
+            if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_tx);
             if (is8)
-              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b8, &s.b_full[sb], (kb - a.kb16) * 128,
+              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb8, &s.b_full[sb], (kb - a.kb16) * 128,
                                tap * a.cout_p + n0);
             else
-              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, &tm_b, &s.b_full[sb], kb * 64,
+              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb, &s.b_full[sb], kb * 64,
                                tap * a.cout_p + n0);
             if (++sb == a.b_stages) {
               sb = 0;
@@ -1813,7 +1827,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // (the whole warp runs the loop -- uniform registers, see umma_f16_p -- and the elected lane issues)
+    if (leader) {
+      const uint32_t lead = elect_one() ? 1u : 0u;
       int sa = 0, sb = 0, stage = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
       const uint32_t a_ring_addr = smem_u32(a_ring), b_region_addr = smem_u32(b_region);
@@ -1823,6 +1839,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int item = pair; item < n_items; item += n_pairs_grid) {
         if (!active(item)) continue;
         const uint32_t d_base = tmem_base + stage * acc_stride;
+        const uint32_t idesc = (item_n(item) == a.n_tiles - 1) ? a.idesc_last : a.idesc;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
           const bool is8 = kb >= a.kb16;
           const int nk = is8 ? ((kb == a.k_blocks - 1) ? nk_last8 : 4) : ((kb == a.kb16 - 1) ? nk_last : 4);
@@ -1844,23 +1861,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (k < nk) {
-                  if (is8) umma_f8_pair(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, 1);
-                  else umma_f16_pair(d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, a.idesc, (kb | tap | k) != 0);
+                  if (is8) umma_f8_pair_p(lead, d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, idesc, 1);
+                  else umma_f16_pair_p(lead, d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, idesc, (kb | tap | k) != 0);
                 }
             }
-            umma_commit_pair(&s.b_empty[sb]);
+            umma_commit_pair_p(lead, &s.b_empty[sb]);
             if (++sb == a.b_stages) {
               sb = 0;
               pb ^= 1;
             }
           }
-          umma_commit_pair(&s.a_empty[sa]);
+          umma_commit_pair_p(lead, &s.a_empty[sa]);
           if (++sa == a.a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-        umma_commit_pair(&s.tmem_full[stage]);
+        umma_commit_pair_p(lead, &s.tmem_full[stage]);
         if (++stage == a.acc_stages) {
           stage = 0;
           acc_phase ^= 1;
@@ -1876,16 +1893,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const bool odd = lane & 1;
     const int row_elems = a.cout_p * a.out_planes;
     const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
-    const int n_chunks = a.n_tile >> 4;
     int stage = 0, it = -1;
     uint32_t acc_phase = 0;
     for (int item = pair; item < n_items; item += n_pairs_grid) {
       if (!active(item)) continue;
       ++it;
       const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM;
-      const int n0 = item_n(item) * a.n_tile;
+      const int n_idx = item_n(item);
+      const int n_cur = (n_idx == a.n_tiles - 1) ? a.n_last : a.n_tile;
+      const int n_chunks = n_cur >> 4;
+      const int n0 = n_idx * a.n_tile;
       float* bias_s = s.bias[it & 1];
-      for (int i = et; i < a.n_tile; i += epi_threads) bias_s[i] = a.bias[n0 + i];
+      for (int i = et; i < n_cur; i += epi_threads) bias_s[i] = a.bias[n0 + i];
       asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
       bool valid[MS], writable[MS];
       int64_t out_row[MS];
@@ -1943,7 +1962,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const ConvArgs);
 PairKernelFn pick_conv_pair(int ms) { return ms == 2 ? conv_pair_kernel<2> : conv_pair_kernel<1>; }
 
 // ------------------------------------------------------------------------------------
@@ -2164,7 +2184,7 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
   m->f8 = (precision == RISER_PREC_F16_F8) ? 1 : 0;
   m->passes = (precision == RISER_PREC_F16 || m->f8) ? 1 : 2;  // fp16 weight planes (hi [, lo])
   m->act_planes = (precision == RISER_PREC_F16_X3 || m->f8) ? 2 : 1;   // activation planes (hi [, lo])
-  m->f8_from = std::max(1, env_int("RISER_F8_FROM", 6));
+  m->f8_from = std::max(1, env_int("RISER_F8_FROM", 5));
   m->device = device;
   cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
   int cin = 1, cin_p = 1;
@@ -2466,15 +2486,25 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fixed + w_eo + static_cast<size_t>(a.a_stages) * a.ms * group1;
       lp.rows_per_super = a.ms * 2 * kBlockM;
     }
-    if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 0)) {
+    if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 1)) {
       // conv_pair_kernel: M = 256 over two CTAs, each holds 128 rows of A and half of every weight tile
+      // N tiles of the pair kernel: 256 wide (the widest M = 256 MMA: fewest shared-memory operand bytes per MAC)
+      // with ONE narrower last tile instead of equal tiles -- cout_p itself (the next layer's K) is unchanged
       lp.pair = 1;
-      int st2 = make_tmap(&lp.tm_b, L.w, L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
-      if (!st2) st2 = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, L.n_tile / 2, false);
+      const int wide = std::max(64, std::min(kMaxNTile, env_int("RISER_PAIR_NTILE", kMaxNTile)) & ~31);
+      a.n_tile = std::min(wide, L.cout_p);
+      a.n_tiles = (L.cout_p + a.n_tile - 1) / a.n_tile;
+      a.n_last = L.cout_p - (a.n_tiles - 1) * a.n_tile;
+      a.acc_cols = round_up(a.n_tile, 32);
+      int st2 = make_tmap(&lp.tm_b, L.w, L.cin_p, 3ull * L.cout_p, a.n_tile / 2, false);
+      if (!st2) st2 = make_tmap8(&lp.tm_b8, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, a.n_tile / 2, false);
+      if (!st2) st2 = make_tmap(&lp.tm_bl, L.w, L.cin_p, 3ull * L.cout_p, a.n_last / 2, false);
+      if (!st2) st2 = make_tmap8(&lp.tm_b8l, L.w8, 2ull * L.cin_p, 2ull * L.cin_p, 3ull * L.cout_p, a.n_last / 2, false);
       if (st2) return st2;
-      a.idesc = umma_idesc_f16(256, L.n_tile);
-      a.ms = (2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 2) >= 2) ? 2 : 1;
-      const size_t a_group = static_cast<size_t>(a.ms) * 136 * 128, half_b = static_cast<size_t>(L.n_tile / 2) * 128;
+      a.idesc = umma_idesc_f16(256, a.n_tile);
+      a.idesc_last = umma_idesc_f16(256, a.n_last);
+      a.ms = (2 * 2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 1) >= 2) ? 2 : 1;   // two accumulator stages first
+      const size_t a_group = static_cast<size_t>(a.ms) * 136 * 128, half_b = static_cast<size_t>(a.n_tile / 2) * 128;
       a.a_stages = env_int("RISER_PAIR_ASTAGES", 3);
       a.b_stages = std::max(2, std::min<int>(kMaxBStages, static_cast<int>((avail - a.a_stages * a_group) / half_b)));
       a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
@@ -2547,6 +2577,20 @@ extern "C" int riser_plan_fused_layer0(const riser_plan* p) { return p ? p->fuse
 
 extern "C" int riser_plan_layer_eo(const riser_plan* p, int i) {
   return (p && i >= 1 && i < p->model->n_layers) ? p->layer[i].eo : 0;
+}
+
+extern "C" int riser_plan_layer_format(const riser_plan* p, int i) {
+  if (!p || i < 1 || i >= p->model->n_layers) return 0;
+  if (p->model->layer[i].f8) return 3;
+  return p->model->act_planes == 2 ? 2 : 1;
+}
+
+extern "C" int riser_plan_layer_kernel(const riser_plan* p, int i) {
+  if (!p || i < 1 || i >= p->model->n_layers) return -1;
+  if (i == 1 && p->fuse_l0 == 2) return 3;
+  if (i == 1 && p->fuse_l0 == 1) return 4;
+  if (p->layer[i].pair) return 2;
+  return p->layer[i].eo ? 1 : 0;
 }
 
 extern "C" int riser_plan_layer_info(const riser_plan* p, int i, int64_t* offset, int* rows_per_read,
@@ -2622,7 +2666,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RISER_CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_conv_pair(a.ms), lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, a));
+    RISER_CUDA_TRY(cudaLaunchKernelEx(&cfg, pick_conv_pair(a.ms), lp.tm_a, lp.tm_b, lp.tm_a8, lp.tm_b8, lp.tm_bl, lp.tm_b8l, a));
     return RISER_OK;
   }
   if (lp.eo) {
@@ -2676,8 +2720,11 @@ extern "C" int riser_forward_stage(const riser_plan* p, int stage, const float* 
     if (p->n_chunked == 0) return launch_layer0(p, x, ld_x, len, 0, p->B, st);
     for (int b0 = 0; b0 < p->B; b0 += p->chunk_reads)
       if ((rc = launch_layer0(p, x, ld_x, len, b0, std::min(p->chunk_reads, p->B - b0), st))) return rc;
+  } else if (stage >= 16 && stage < 16 + m->n_layers) {   // conv layer (stage - 16) alone (timing aid: tools/layer_events.py)
+    RISER_REQUIRE(stage - 16 >= 1 && p->n_chunked == 0, "riser_forward_stage: single-layer stages need layer >= 1, no chunking");
+    return launch_conv(p, stage - 16, x, ld_x, len, 0, p->B, st);
   } else {
-    return fail(RISER_EINVAL, "riser_forward_stage: stage %d outside 0..3", stage);
+    return fail(RISER_EINVAL, "riser_forward_stage: stage %d outside 0..3 / 16..", stage);
   }
   return RISER_OK;
 }

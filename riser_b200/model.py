@@ -45,8 +45,21 @@ class Plan:
                    "riser_plan_layer_info")
         return off.value, rows.value, cp.value, c.value, nt.value
 
-    def activation(self, i, n_layers, planes=1):
-        """Layer i's input buffer as a [B, rows_per_read, channels] tensor view (tests)."""
+    def layer_format(self, i):
+        """Row format of layer i's input buffer: 1 = fp16, 2 = fp16 hi | lo, 3 = fp16 hi | e4m3 a | e4m3 lo (0: head)."""
+        return int(_lib.lib().riser_plan_layer_format(self._handle, i))
+
+    def layer_kernel(self, i):
+        """Name of the kernel that runs conv layer i in this plan (riser_plan_layer_kernel)."""
+        k = int(_lib.lib().riser_plan_layer_kernel(self._handle, i))
+        return {0: "conv_tc_kernel", 1: "conv_eo_kernel", 2: "conv_pair_kernel", 3: "fused01_kernel",
+                4: "conv_tc_kernel<FUSED>"}.get(k, "?")
+
+    def activation(self, i, n_layers, planes=None):
+        """Layer i's input buffer as a [B, rows_per_read, channels] tensor (tests); `planes` = row format,
+        by default the one the plan reports (layer_format)."""
+        if planes is None:
+            planes = self.layer_format(i) or 1
         off, rows, cp, c, _ = self.layer_info(i)
         dt = torch.float32 if i == n_layers else torch.float16
         nbytes = self.B * rows * cp * (4 if i == n_layers else 2)

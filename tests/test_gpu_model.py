@@ -53,17 +53,24 @@ def oracle_layers(state, x):
                                             (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8),
                                             (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3)),
                                             (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat")),
-                                            (2, (PREC_F16_F8, "pair"))])
+                                            (2, (PREC_F16_F8, "nopair")), (2, (PREC_F16_F8, "pair2")),
+                                            (2, (PREC_F16_F8, "pair192")), (2, (PREC_F16_F8, 6))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
-    f8_from = 6                      # F16_F8: first layer that runs the e4m3 correction pass (default 6)
     if isinstance(precision, tuple) and precision[1] == "flat":     # without the even / odd plane layout
         precision = precision[0]
         monkeypatch.setenv("RISER_EO", "0")
-    elif isinstance(precision, tuple) and precision[1] == "pair":   # layers 6-11 on CTA pairs (cta_group::2), opt-in
+    elif isinstance(precision, tuple) and precision[1] == "nopair":   # e4m3 layers on single CTAs (conv_tc_kernel<F8>)
+        precision = precision[0]                                       # instead of CTA pairs (cta_group::2, the default)
+        monkeypatch.setenv("RISER_PAIR", "0")
+    elif isinstance(precision, tuple) and precision[1] == "pair2":    # CTA pairs, two 256-row sub-tiles per item
         precision = precision[0]
-        monkeypatch.setenv("RISER_PAIR", "1")
-    elif isinstance(precision, tuple):
+        monkeypatch.setenv("RISER_PAIR_MS", "2")                      # (needs N tiles <= 128: two accumulator stages)
+        monkeypatch.setenv("RISER_PAIR_NTILE", "128")
+    elif isinstance(precision, tuple) and precision[1] == "pair192":  # CTA pairs, 192-wide N tiles (+ narrower last)
+        precision = precision[0]
+        monkeypatch.setenv("RISER_PAIR_NTILE", "192")
+    elif isinstance(precision, tuple):                                # first layer that runs the e4m3 correction pass
         precision, f8_from = precision
         monkeypatch.setenv("RISER_F8_FROM", str(f8_from))
     rng = np.random.default_rng(0)
@@ -81,8 +88,7 @@ def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     for b, v in enumerate(normed):
         want = oracle_layers(state, torch.from_numpy(np.asarray(v, dtype=np.float64)).float())
         for i in range(2 if plan.fused_layer0 else 1, 13):
-            planes = {PREC_F16_X3: 2, PREC_F16_F8: 3 if i >= f8_from else 2}.get(precision, 1)
-            act = plan.activation(i, 12, planes=planes)[b].float().cpu()
+            act = plan.activation(i, 12)[b].float().cpu()          # decoded by the row format the plan reports
             w = want[i - 1].T                                  # [L_i, C]
             L = w.shape[0]
             err = (act[:L] - w).abs().max().item()

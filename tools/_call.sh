@@ -1,8 +1,17 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_pipeline.py tests/test_gpu_resnet.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/r2l_tests.log
-python bench.py --no-cpu-baseline > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 130 --csv --log-file gpurun_out/r2l_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-for lib in riser_b200/libriser_b200.so build_ab/replay.so; do echo $lib >> gpurun_out/r2l_time_resnet.log; RISER_B200_LIB=$lib timeout 120 python tools/time_resnet.py 512 12048 basic >> gpurun_out/r2l_time_resnet.log 2>&1; done
-timeout 120 python tools/time_resnet.py 4096 12048 basic >> gpurun_out/r2l_time_resnet.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2l_resnet_launches.csv python tools/time_resnet.py 512 12048 basic > /dev/null 2>&1
-cat gpurun_out/r2l_tests.log gpurun_out/r2l_time_resnet.log; cut -c1-160 gpurun_out/r2l_bench.json
+T=r2o
+LE="python tools/layer_events.py 4096 16000 3 12"
+for rep in 1 2; do
+RISER_PAIR=0 RISER_F8_FROM=6 $LE single_f6 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR=1 RISER_F8_FROM=6 $LE pair_f6 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR=1 RISER_F8_FROM=5 $LE pair_f5 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR=0 RISER_F8_FROM=5 $LE single_f5 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+done
+RISER_PAIR=1 RISER_F8_FROM=6 RISER_PAIR_NTILE=192 $LE pair_f6_nt192 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+for v in 1 2 16 32; do RISER_B200_LIB=build_ab/dbg$v.so RISER_PAIR=0 RISER_F8_FROM=6 $LE dbg$v >> gpurun_out/${T}_layers.jsonl 2>/dev/null; done
+for rep in 1 2; do
+RISER_PAIR=0 RISER_F8_FROM=6 python bench.py --no-cpu-baseline --steps 20 >> gpurun_out/${T}_bench_single_f6.jsonl 2>/dev/null
+RISER_PAIR=1 RISER_F8_FROM=6 python bench.py --no-cpu-baseline --steps 20 >> gpurun_out/${T}_bench_pair_f6.jsonl 2>/dev/null
+done
+cat gpurun_out/${T}_layers.jsonl | cut -c1-400
+cut -c1-160 gpurun_out/${T}_bench_*.jsonl
