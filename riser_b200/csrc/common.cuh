@@ -312,6 +312,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// The same without release semantics: a "this TMEM accumulator is drained" signal orders nothing but the warp's
+// tcgen05.ld (already complete: tcgen05.wait::ld + fence::before_thread_sync), whereas the .release.cluster form
+// compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. it waits for every global store the epilogue warp has in flight --
+// 22 % of all stall samples of conv_pair_kernel in layer 6 (profiles/README.md, round 2).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
 // TMA tile load issued by either CTA of a pair into ITS OWN shared memory; completion (bytes) is
 // signalled on the LEADER's mbarrier at the same offset.
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint64_t* bar,

@@ -912,19 +912,19 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
 // are row-shifted views of the two tiles accumulated into two column ranges of the same lane.
 //
 // Work item = 255 pooled layer-1 outputs (pair indices u0 .. u0+254; E rows 0..255 = E[u0+i],
-// O rows 0..255 = O[u0+i-1]).  Roles (20 warps):
+// O rows 0..255 = O[u0+i-1]).  Roles (22 warps):
 //   warp 0        producer: bulk copies (TMA) of the item's signal segment into a 4-stage ring
-//   warps 2,3     cvt1: signal (shared memory) -> layer-0 A rows in shared memory
+//   warps 2..5    cvt1: signal (shared memory) -> layer-0 A rows in shared memory
 //   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
-//   warps 4..11   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
-//   warps 12..19  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
+//   warps 6..13   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
+//   warps 14..21  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
 constexpr int kF2Pairs = 255;
-constexpr int kF2Threads = 640;
+constexpr int kF2Threads = 704;
 constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shifted taps of row 255 touch
 constexpr uint32_t kF2A0Tile = 256 * 64;   // per row: [E window (K=16) | O window (K=16)]
 constexpr int kF2N0 = 48;
 constexpr int kF2D0Col = 256;              // TMEM: layer-1 accumulators [0,256), layer-0 at 256 + 48*k
-constexpr int kF2CvtThreads = 64;
+constexpr int kF2CvtThreads = 128;     // four cvt1 warps (two were ~100 % busy: the stage that paced the launch)
 constexpr int kF2XStages = 4;
 constexpr int kF2MaxLocalItems = 2048;   // work items per CTA whose activity flags fit the shared-memory copy
 constexpr uint32_t kF2XStage = 260 * 16;     // pairs i = -2 .. 256 (4 samples each) + pad
@@ -993,10 +993,10 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
     mbar_init(&s.w_full, 1);
     for (int i = 0; i < kF2XStages; ++i) {
       mbar_init(&s.x_full[i], 1);
-      mbar_init(&s.x_empty[i], 2);
+      mbar_init(&s.x_empty[i], kF2CvtThreads / 32);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s.a0_full[i], 2);
+      mbar_init(&s.a0_full[i], kF2CvtThreads / 32);
       mbar_init(&s.a0_empty[i], 1);
       mbar_init(&s.d0_full[i], 1);
       mbar_init(&s.d0_empty[i], 4);
@@ -1188,9 +1188,9 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         cur = nxt;
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 2 + kF2CvtThreads / 32) {
     // ===================== cvt1: signal -> layer-0 A rows =====================
-    const int ct = (warp - 2) * 32 + lane;      // 0..63
+    const int ct = (warp - 2) * 32 + lane;      // 0..kF2CvtThreads-1
     const __half2 one2 = __floats2half2_rn(1.f, 1.f);
     F2Iter iter(flags_l, n_items);
     int k = 0;
@@ -1259,10 +1259,10 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         mbar_arrive(&s.a0_full[st]);
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < 10 + kF2CvtThreads / 32) {
     // ===================== mid-epilogue: layer-0 accumulators -> layer-1 A tiles =====================
     const int q = warp & 3;
-    const int h = (warp - 4) >> 2;                      // 0: E sub-tiles, 1: O sub-tiles
+    const int h = (warp - 2 - kF2CvtThreads / 32) >> 2;       // 0: E sub-tiles, 1: O sub-tiles
     F2Iter iter(flags_l, n_items);
     int k = 0;
     for (int item = iter.take(); item >= 0; item = iter.take(), ++k) {
@@ -1358,7 +1358,7 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
   } else {
     // ===================== epilogue: layer-1 accumulators -> act_2 =====================
     const int q = warp & 3;
-    const int sub = (warp - 12) >> 2;
+    const int sub = (warp - 10 - kF2CvtThreads / 32) >> 2;
     const int row_elems = a.cout_p * a.out_planes;
     const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
     const float inv_scale = a.w_inv_scale;
@@ -1717,7 +1717,7 @@ EoKernelFn pick_conv_eo(int ms, int planes, int wplanes) {
 // accumulators on the leader's barrier (mapa + remote arrive).
 // Work item of a pair = (MS sub-tiles of 256 flat rows, N tile); both CTAs walk the same item list.
 template <int MS>
-__global__ void __launch_bounds__(64 + 128 * kMaxEpiSets, 1)
+__global__ void __launch_bounds__(96 + 128 * kMaxEpiSets, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_b8,
                  const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_b8l,
@@ -1745,17 +1745,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b8);
     tma_prefetch_desc(&tm_bl);
     tma_prefetch_desc(&tm_b8l);
+    const uint32_t n_issuers = a.dual ? 2 : 1;     // every issuer's commit arrives on the operand "empty" barriers
     for (int i = 0; i < a.a_stages; ++i) {
       mbar_init(&s.a_full[i], 1);
-      mbar_init(&s.a_empty[i], 1);
+      mbar_init(&s.a_empty[i], n_issuers);
     }
     for (int i = 0; i < a.b_stages; ++i) {
       mbar_init(&s.b_full[i], 1);
-      mbar_init(&s.b_empty[i], 1);
+      mbar_init(&s.b_empty[i], n_issuers);
     }
     for (int i = 0; i < a.acc_stages; ++i) {
-      mbar_init(&s.tmem_full[i], 1);
-      for (int ms = 0; ms < MS; ++ms) mbar_init(&s.tmem_empty[i][ms], 2 * 4 * a.epi_sets);   // both CTAs' warps
+      for (int ms = 0; ms < MS; ++ms) {
+        mbar_init(&s.tmem_full_ms[i][ms], 1);
+        mbar_init(&s.tmem_empty[i][ms], 2 * 4 * a.epi_sets);   // both CTAs' warps
+      }
     }
     fence_mbar_init();
   }
@@ -1825,10 +1828,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    // (the whole warp runs the loop -- uniform registers, see umma_f16_p -- and the elected lane issues)
+  } else if (warp == 1 || (a.dual && warp == 2 + 4 * a.epi_sets)) {
+    // ===================== MMA issuer(s) (leader CTA only) =====================
+    // One warp issues every MMA of an item -- or, `dual` (MS == 2), one warp PER SUB-TILE: with 2 x 256 accumulator
+    // columns the TMEM holds one item, so a single issuer would idle for the whole drain of both sub-tiles; the two
+    // issuers walk the same operand stages on their own (both commit to the "empty" barriers), and the one whose
+    // accumulator is still being drained falls a few weight tiles behind while the other keeps the tensor pipe busy.
+    // (The whole warp runs the loop -- uniform registers, see umma_f16_p -- and the elected lane issues.)
     if (leader) {
+      const int ms_lo = a.dual ? (warp == 1 ? 0 : 1) : 0;
+      const int ms_hi = a.dual ? ms_lo + 1 : MS;
       const uint32_t lead = elect_one() ? 1u : 0u;
       int sa = 0, sb = 0, stage = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
@@ -1853,6 +1862,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint64_t db = sw_desc<false>(b_region_addr + sb * b_bytes);
 #pragma unroll
             for (int ms = 0; ms < MS; ++ms) {
+              if (ms < ms_lo || ms >= ms_hi) continue;      // (the other issuer's sub-tile)
               if (kb == 0 && tap == 0) {       // first touch of this accumulator: both CTAs have drained it
                 mbar_wait(&s.tmem_empty[stage][ms], acc_phase ^ 1);
                 tc_fence_after();
@@ -1877,7 +1887,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             pa ^= 1;
           }
         }
-        umma_commit_pair_p(lead, &s.tmem_full[stage]);
+#pragma unroll
+        for (int ms = 0; ms < MS; ++ms)
+          if (ms >= ms_lo && ms < ms_hi) umma_commit_pair_p(lead, &s.tmem_full_ms[stage][ms]);
         if (++stage == a.acc_stages) {
           stage = 0;
           acc_phase ^= 1;
@@ -1922,11 +1934,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           out_row[ms] = static_cast<int64_t>(b) * a.Lp_out + tp;
         }
       }
-      mbar_wait_relaxed(&s.tmem_full[stage], acc_phase);
-      tc_fence_after();
       int u = eset;
 #pragma unroll
       for (int ms = 0; ms < MS; ++ms) {
+        mbar_wait_relaxed(&s.tmem_full_ms[stage][ms], acc_phase);      // this sub-tile's accumulator is complete
+        tc_fence_after();
         void* orow = a.out_fp32
                          ? static_cast<void*>(static_cast<float*>(a.out) + out_row[ms] * row_elems + n0)
                          : static_cast<void*>(static_cast<__half*>(a.out) + out_row[ms] * row_elems + n0);
@@ -1944,7 +1956,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&s.tmem_empty[stage][ms], 0);   // on the leader's barrier
+        if (lane == 0) mbar_arrive_remote_relaxed(&s.tmem_empty[stage][ms], 0);   // on the leader's barrier
       }
       if (++stage == a.acc_stages) {
         stage = 0;
@@ -2486,7 +2498,8 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.smem = fixed + w_eo + static_cast<size_t>(a.a_stages) * a.ms * group1;
       lp.rows_per_super = a.ms * 2 * kBlockM;
     }
-    if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 1)) {
+    if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 1) &&
+        i >= env_int("RISER_PAIR_FROM", 6)) {
       // conv_pair_kernel: M = 256 over two CTAs, each holds 128 rows of A and half of every weight tile
       // N tiles of the pair kernel: 256 wide (the widest M = 256 MMA: fewest shared-memory operand bytes per MAC)
       // with ONE narrower last tile instead of equal tiles -- cout_p itself (the next layer's K) is unchanged
@@ -2503,11 +2516,17 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       if (st2) return st2;
       a.idesc = umma_idesc_f16(256, a.n_tile);
       a.idesc_last = umma_idesc_f16(256, a.n_last);
-      a.ms = (2 * 2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 1) >= 2) ? 2 : 1;   // two accumulator stages first
+      // One 256-row sub-tile per item and two accumulator stages is the measured optimum (layers 6-11 in situ: 0.38 /
+      // 0.47 / 0.37 / 0.38 / 0.46 / 0.49 ms against 0.41 / 0.47 / 0.40 / 0.43 / 0.48 / 0.55 with two sub-tiles, which
+      // halve the weight bytes streamed per MAC but leave the TMEM one item deep; `dual` then gives each sub-tile its
+      // own issuing warp so that one computes while the other is drained -- RISER_PAIR_MS=2 keeps that variant testable).
+      a.ms = (2 * a.acc_cols <= kTmemCols && env_int("RISER_PAIR_MS", 1) >= 2) ? 2 : 1;
       const size_t a_group = static_cast<size_t>(a.ms) * 136 * 128, half_b = static_cast<size_t>(a.n_tile / 2) * 128;
-      a.a_stages = env_int("RISER_PAIR_ASTAGES", 3);
+      a.a_stages = std::max(2, std::min(kMaxAStages, env_int("RISER_PAIR_ASTAGES", a.ms == 2 ? 3 : 5)));
+      while (a.a_stages > 2 && a.a_stages * a_group + 4 * half_b > avail) --a.a_stages;
       a.b_stages = std::max(2, std::min<int>(kMaxBStages, static_cast<int>((avail - a.a_stages * a_group) / half_b)));
       a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
+      a.dual = (a.ms == 2 && env_int("RISER_DUAL_ISSUE", 1)) ? 1 : 0;
       a.epi_sets = 4;
       lp.smem = fixed + a.a_stages * a_group + a.b_stages * half_b;
       lp.rows_per_super = a.ms * 256;
@@ -2656,7 +2675,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
     cudaLaunchConfig_t cfg = {};
     const int n_items = a.n_supers * a.n_tiles;
     cfg.gridDim = dim3(static_cast<unsigned>(std::min(2 * n_items, p->model->sm_count & ~1)));
-    cfg.blockDim = dim3(64 + 128 * a.epi_sets);
+    cfg.blockDim = dim3(64 + 128 * a.epi_sets + (a.dual ? 32 : 0));
     cfg.dynamicSmemBytes = lp.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

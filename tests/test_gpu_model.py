@@ -53,7 +53,7 @@ def oracle_layers(state, x):
                                             (2, PREC_F16_X3), (0, PREC_F16_F8), (2, PREC_F16_F8),
                                             (0, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 1)), (2, (PREC_F16_F8, 3)),
                                             (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat")),
-                                            (2, (PREC_F16_F8, "nopair")), (2, (PREC_F16_F8, "pair2")),
+                                            (2, (PREC_F16_F8, "nopair")), (2, (PREC_F16_F8, "pair2")), (2, (PREC_F16_F8, "pair5")),
                                             (2, (PREC_F16_F8, "pair192")), (2, (PREC_F16_F8, 6))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
@@ -63,10 +63,14 @@ def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     elif isinstance(precision, tuple) and precision[1] == "nopair":   # e4m3 layers on single CTAs (conv_tc_kernel<F8>)
         precision = precision[0]                                       # instead of CTA pairs (cta_group::2, the default)
         monkeypatch.setenv("RISER_PAIR", "0")
-    elif isinstance(precision, tuple) and precision[1] == "pair2":    # CTA pairs, two 256-row sub-tiles per item
+    elif isinstance(precision, tuple) and precision[1] == "pair2":    # CTA pairs, two 256-row sub-tiles per item,
+        precision = precision[0]                                       # one issuing warp each (default: one sub-tile)
+        monkeypatch.setenv("RISER_PAIR_MS", "2")
+    elif isinstance(precision, tuple) and precision[1] == "pair5":    # CTA pairs from layer 5 on, one issuing warp
         precision = precision[0]
-        monkeypatch.setenv("RISER_PAIR_MS", "2")                      # (needs N tiles <= 128: two accumulator stages)
-        monkeypatch.setenv("RISER_PAIR_NTILE", "128")
+        monkeypatch.setenv("RISER_PAIR_FROM", "5")
+        monkeypatch.setenv("RISER_PAIR_MS", "2")
+        monkeypatch.setenv("RISER_DUAL_ISSUE", "0")
     elif isinstance(precision, tuple) and precision[1] == "pair192":  # CTA pairs, 192-wide N tiles (+ narrower last)
         precision = precision[0]
         monkeypatch.setenv("RISER_PAIR_NTILE", "192")

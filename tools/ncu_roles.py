@@ -12,7 +12,9 @@ for spec in sys.argv[3:]:
     name, rng = spec.split(":")
     lo, hi = rng.split("-")
     roles.append((name, int(lo), int(hi)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+import os
+sel = (["-s", os.environ["NCU_LAUNCH"], "-c", "1"] if os.environ.get("NCU_LAUNCH") else [])   # one launch of the report
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel,
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 cur, hdr = None, None
