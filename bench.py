@@ -110,7 +110,7 @@ def pass_equivalents(length, precision, formats):
         f = 2 * 3 * cin * c * l
         if i >= 1:
             tot += f
-            w += f * {1: 2.0, 2: 3.0, 3: 2.0}[formats[i]]
+            w += f * {1: 2.0, 2: 3.0, 3: 2.0, -1: 3.0}[formats[i]]    # (-1: fused into the previous launch, hi + lo planes)
         cin, l = c, l // 2
     return w / tot
 
@@ -673,7 +673,8 @@ def main():
                                       f"layers {f8_layers[0] if f8_layers else '-'}-11, the other conv layers as mode 2; "
                                       "f32 accumulate; layer 0 and the head in f32, normalise in f64"}[precision],
                     "chunk": clf.chunk, "decisions_made": n_dec},
-            "roofline": {"bound": "tensor", "kernel": kern_desc + " -- %d launches per forward" % (len(CHANNELS) - (1 if fused else 0)),
+            "roofline": {"bound": "tensor", "kernel": kern_desc + " -- %d launches per forward" % len({(k, tuple(v)) if k in ("fused01_kernel", "conv_eo2_kernel") else (k, i)
+                                                                                      for k, v in kern.items() for i in v}),
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                          "traffic": traffic, "traffic_source": tsrc, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "frac_burst": achieved / burst_peak(), "peak_burst": burst_peak(),

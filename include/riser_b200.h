@@ -216,14 +216,16 @@ int riser_plan_layer_eo(const riser_plan* p, int i);
  *   2 = fp16 hi | fp16 lo planes (a = hi + lo; the F16_X3 terms W_hi*a_hi + W_lo*a_hi + W_hi*a_lo);
  *   3 = fp16 hi | e4m3(a) | e4m3((a - hi) * 2^9): the operands of the fp16 pass and of the single
  *       e4m3 correction pass of RISER_PREC_F16_F8 (same bytes per row as format 2).
- * 0 for i outside that range.  Tests decode activations with it; bench.py derives the tensor passes
+ * 0 for i outside that range, -1 when the buffer is never materialised (layer i is computed inside layer
+ * i - 1's launch: conv_eo2_kernel).  Tests decode activations with it; bench.py derives the tensor passes
  * executed per algorithmic FLOP from it (riser/nets/cnn.py:55-64 is one fp32 pass).            */
 int riser_plan_layer_format(const riser_plan* p, int i);
 
 /* Which kernel runs conv layer i (1..n_layers-1) in this plan: 0 = conv_tc_kernel (one CTA per SM),
  * 1 = conv_eo_kernel (even / odd planes, resident weights), 2 = conv_pair_kernel (cta_group::2 CTA
  * pairs), 3 = fused01_kernel (layers 0 + 1 in one launch), 4 = conv_tc_kernel with the CUDA-core
- * layer-0 converter warps.  -1 outside the range.  For bench.py's launch description.          */
+ * layer-0 converter warps, 5 = conv_eo2_kernel (this layer and its neighbour in one launch, the
+ * activation between them kept in shared memory).  -1 outside the range.  For bench.py's launch description. */
 int riser_plan_layer_kernel(const riser_plan* p, int i);
 
 /* Replaces the decision rule of riser/control.py:75-82 for M models:

@@ -137,6 +137,23 @@ struct ConvArgs {
   uint32_t idesc_last;
 };
 
+// conv_eo2_kernel (two even / odd layers in one launch; see the kernel)
+struct Eo2Args {
+  const float* bias1;
+  const float* bias2;
+  const int32_t* len0;
+  void* out;
+  int B, n_seg;                 // items = B * n_seg (segment fastest)
+  int half_lp_in;               // pairs per read in the first layer's input planes
+  int Lp_out, half_lp_out, n_pairs_out, out_eo, out_f8, out_planes, cout_p2;
+  int shift1, shift2;           // valid rows: len0 >> shift1 (intermediate), len0 >> shift2 (output)
+  int cin_p1, n1, n2;           // first layer's padded input channels; N tiles (= padded Cout) of the two layers
+  int kb1, kb2;                 // 32-channel K blocks
+  int acc1, acc2;               // TMEM columns per accumulator: [even n | odd n] rounded to 32
+  uint32_t idesc1_n, idesc1_2n, idesc2_n, idesc2_2n;
+  float inv_scale1, inv_scale2;
+};
+
 struct ActivityLayer {
   int Lp_in, rows_in, rows_per_super, shift, n_supers, flag_off;
 };
@@ -150,6 +167,10 @@ struct LayerPlan {
   CUtensorMap tm_bl, tm_b8l;              // conv_pair_kernel: weight maps whose box is half of the LAST N tile
   int eo = 0;                             // input in the even / odd plane layout -> conv_eo_kernel
   int pair = 0;                           // CTA pairs (cta_group::2) -> conv_pair_kernel
+  int fuse_next = 0;                      // this layer and the next one run as ONE conv_eo2_kernel launch
+  int fused_prev = 0;                     // computed inside the previous layer's launch: its input buffer is never written
+  Eo2Args eo2;                            // fuse_next: arguments of the two-layer launch
+  size_t eo2_smem = 0;
   ConvArgs args;
   int n_supers_total = 0;
   int rows_per_super = 0;   // flat input rows one work item covers (ms * 128; 510 for the fused layers 0+1)
@@ -1705,6 +1726,361 @@ EoKernelFn pick_conv_eo(int ms, int planes, int wplanes) {
 }
 
 // ------------------------------------------------------------------------------------
+// Two narrow layers in ONE launch ("EO2", layers 2 + 3 of the shipped network): the activation between them never
+// exists in HBM (3.1 GB of the 16 GB the conv stack moved per 4096 x 16,000 forward, and the two layers it sat
+// between were HBM-bound: 5.7 and 4.9 TB/s).  Both layers keep the even / odd row scheme of conv_eo_kernel.
+//
+// Work item = (read b, segment s): 127 rows j = 127 s + l of the SECOND layer's pooled output.  They need the
+// first layer's output rows 2j - 1 .. 2j + 2, i.e. r in [254 s - 1, 254 s + 255): exactly two 128-lane tiles of the
+// first layer (A: r = c + l with c = 254 s - 1, B: c + 128), whose inputs the producer takes from the E / O planes
+// in HBM by TMA at any offset (rows before the read's start or beyond its end feed lanes that are masked to zero,
+// which is also what gives the convolution its 'same' padding).  A mid-epilogue drains the first layer's
+// accumulators (max-pool in-lane, bias, ReLU, length mask, fp16 hi + lo split) into the SECOND layer's operand
+// tiles in shared memory -- row r goes to the E tile (even r, index r / 2 - 127 s) or the O tile (odd r, index
+// (r - 1) / 2 - 127 s + 1), in the SWIZZLE_64B K-major layout a TMA load would have produced -- and the second layer
+// runs 127 valid lanes (lane 127 reads the slack row 128 of both tiles and is discarded).  Halo recomputed: 2 of
+// 256 first-layer rows per item.
+//
+// Roles (18 warps): warp 0 TMA producer (weights of both layers once, then a 2-stage ring of first-layer input
+// tiles), warp 1 MMA issuer, warps 2-5 / 6-9 mid-epilogue of tile A / tile B, warps 10-17 final epilogue (two
+// sets splitting the 16-column chunks).  Issue order: ..., first layer of item k + 1 (two tiles), second layer of
+// item k, ...: the mid-epilogue of item k + 1 runs while the tensor pipe works on the second layer of item k and
+// the first layer of item k + 2, the one copy of the intermediate tiles being handed back by the commit behind the
+// second layer's MMAs.  TMEM: three first-layer accumulator slots (a tile waits there for the intermediate
+// tiles to come free) + one second-layer accumulator.
+constexpr int kE2Threads = 576;
+constexpr int kE2Rows = 127;              // second-layer output rows per item
+constexpr int kE2MaxLocalItems = 4096;    // work items per CTA whose activity flags fit the shared-memory copy
+
+struct Eo2Smem {
+  uint64_t w_full;
+  uint64_t in_full[2], in_empty[2];
+  uint64_t acc1_full[3], acc1_empty[3];
+  uint64_t a3_full, a3_empty;
+  uint64_t acc2_full, acc2_empty;
+  uint32_t tmem_base;
+  alignas(16) float bias1[128];
+  alignas(16) float bias2[128];
+  uint8_t my_flags[kE2MaxLocalItems];   // activity of this CTA's items (item = blockIdx.x + i * gridDim.x)
+};
+
+// Active items of this CTA in order (flags staged in shared memory once: no global load in the single-thread roles).
+struct Eo2Iter {
+  const uint8_t* local;
+  int i, item, n_items, step;
+  __device__ __forceinline__ Eo2Iter(const uint8_t* l, int n) : local(l), i(0), item(blockIdx.x), n_items(n), step(gridDim.x) {}
+  __device__ __forceinline__ int take() {
+    while (item < n_items) {
+      const int cur = item;
+      const bool f = local ? (local[i] != 0) : true;
+      item += step;
+      ++i;
+      if (f) return cur;
+    }
+    return -1;
+  }
+};
+
+__global__ void __launch_bounds__(kE2Threads, 1)
+conv_eo2_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_o,
+                const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_b2, const Eo2Args a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t b1_bytes = a.n1 * 64, b2_bytes = a.n2 * 64;
+  const uint32_t w1_bytes = 2u * a.kb1 * 3 * b1_bytes, w2_bytes = 2u * a.kb2 * 3 * b2_bytes;
+  const uint32_t in_stage = a.kb1 * 4 * kEoTile;            // [kb][plane][E, O]
+  const uint32_t a3_bytes = a.kb2 * 4 * kEoTile;
+  unsigned char* w1 = base;
+  unsigned char* w2 = w1 + w1_bytes;
+  unsigned char* in_ring = w2 + w2_bytes;
+  unsigned char* a3 = in_ring + 2 * in_stage;
+  Eo2Smem& s = *reinterpret_cast<Eo2Smem*>(a3 + a3_bytes);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  const int n_items = a.B * a.n_seg;
+  const bool use_flags = (n_items + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) <= kE2MaxLocalItems;
+  const uint8_t* flags_l = use_flags ? s.my_flags : nullptr;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_e);
+    tma_prefetch_desc(&tm_o);
+    tma_prefetch_desc(&tm_b1);
+    tma_prefetch_desc(&tm_b2);
+    mbar_init(&s.w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.in_full[i], 1);
+      mbar_init(&s.in_empty[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&s.acc1_full[i], 1);
+      mbar_init(&s.acc1_empty[i], 4);
+    }
+    mbar_init(&s.a3_full, 8);
+    mbar_init(&s.a3_empty, 1);
+    mbar_init(&s.acc2_full, 1);
+    mbar_init(&s.acc2_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&s.tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  // intermediate tiles: the slack rows (128..135) and the padded channels of the last K block are never written again
+  for (uint32_t i = threadIdx.x; i < a3_bytes / 16; i += kE2Threads) reinterpret_cast<uint4*>(a3)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 128; i += kE2Threads) {
+    s.bias1[i] = (i < a.n1) ? a.bias1[i] : 0.f;
+    s.bias2[i] = (i < a.n2) ? a.bias2[i] : 0.f;
+  }
+  if (use_flags)
+    for (int i = threadIdx.x, it = blockIdx.x + threadIdx.x * gridDim.x; it < n_items; i += kE2Threads, it += kE2Threads * gridDim.x) {
+      const int b = it / a.n_seg, sg = it - b * a.n_seg;
+      s.my_flags[i] = (kE2Rows * sg <= (__ldg(a.len0 + b) >> a.shift2)) ? 1 : 0;    // "<=": the zero row that ends the read
+    }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&s.w_full, w1_bytes + w2_bytes);
+      // taps in REVERSE order (slot 2 - tap): [w2; w1] and [w1; w0] are contiguous B operands (see conv_eo_kernel)
+      for (int wp = 0; wp < 2; ++wp)
+        for (int kb = 0; kb < a.kb1; ++kb)
+          for (int tap = 0; tap < 3; ++tap)
+            tma_load_2d(w1 + static_cast<size_t>((wp * a.kb1 + kb) * 3 + 2 - tap) * b1_bytes, &tm_b1, &s.w_full, kb * 32,
+                        (wp * 3 + tap) * a.n1);
+      for (int wp = 0; wp < 2; ++wp)
+        for (int kb = 0; kb < a.kb2; ++kb)
+          for (int tap = 0; tap < 3; ++tap)
+            tma_load_2d(w2 + static_cast<size_t>((wp * a.kb2 + kb) * 3 + 2 - tap) * b2_bytes, &tm_b2, &s.w_full, kb * 32,
+                        (wp * 3 + tap) * a.n2);
+      Eo2Iter iter(flags_l, n_items);
+      uint32_t q = 0;                       // first-layer tiles loaded so far
+      for (int item = iter.take(); item >= 0; item = iter.take()) {
+        const int b = item / a.n_seg, sg = item - b * a.n_seg;
+        const int c0 = 2 * kE2Rows * sg - 1;
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t, ++q) {
+          const uint32_t st = q & 1;
+          mbar_wait(&s.in_empty[st], ((q >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&s.in_full[st], in_stage);
+          unsigned char* dst = in_ring + st * in_stage;
+          const int u = b * a.half_lp_in + c0 + kBlockM * t;        // pair index of lane 0's E row
+          for (int kb = 0; kb < a.kb1; ++kb)
+#pragma unroll
+            for (int ap = 0; ap < 2; ++ap) {
+              unsigned char* tl = dst + static_cast<size_t>((kb * 2 + ap) * 2) * kEoTile;
+              tma_load_2d(tl, &tm_e, &s.in_full[st], ap * a.cin_p1 + kb * 32, u);                 // E[c ..]
+              tma_load_2d(tl + kEoTile, &tm_o, &s.in_full[st], ap * a.cin_p1 + kb * 32, u - 1);   // O[c - 1 ..]
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // (the whole warp runs the loop -- uniform registers -- and the elected lane issues)
+    const bool leader = elect_one();
+    mbar_wait(&s.w_full, 0);
+    tc_fence_after();
+    const uint32_t w1_addr = smem_u32(w1), w2_addr = smem_u32(w2), in_addr = smem_u32(in_ring), a3_addr = smem_u32(a3);
+    const int nk_last1 = (a.cin_p1 - (a.kb1 - 1) * 32) / 16, nk_last2 = (a.n1 - (a.kb2 - 1) * 32) / 16;
+    // One even / odd tile: E[j] x [w1; w0] and O[j] x [w2; w1] feed both conv positions (N = 2n), O[j-1] x w0 the
+    // even and E[j+1] x w2 the odd one (N = n); hi x W_hi, lo x W_hi, hi x W_lo (W_lo only meets the hi plane).
+    auto issue_tile = [&](uint32_t tiles, uint32_t w_addr, uint32_t b_bytes, int kbs, int nk_last, uint32_t d_even,
+                          uint32_t n, uint32_t idesc_n, uint32_t idesc_2n) {
+      const uint32_t d_odd = d_even + n;
+      for (int kb = 0; kb < kbs; ++kb) {
+        const int nk = (kb == kbs - 1) ? nk_last : 2;
+#pragma unroll
+        for (int wp = 0; wp < 2; ++wp) {
+          const uint32_t w_set = w_addr + ((wp * kbs + kb) * 3) * b_bytes;      // slots: w2, w1, w0
+#pragma unroll
+          for (int ap = 0; ap < (wp == 0 ? 2 : 1); ++ap) {
+            const uint32_t e_rows = tiles + ((kb * 2 + ap) * 2) * kEoTile, o_rows = e_rows + kEoTile;
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                if (k < nk) {
+                  const uint64_t w21 = sw_desc<true>(w_set) + 2 * k;
+                  const uint64_t w10 = sw_desc<true>(w_set + b_bytes) + 2 * k;
+                  const uint64_t w0 = sw_desc<true>(w_set + 2 * b_bytes) + 2 * k;
+                  umma_f16(d_even, sw_desc<true>(e_rows) + 2 * k, w10, idesc_2n, (kb | wp | ap | k) != 0);   // E[j]
+                  umma_f16(d_even, sw_desc<true>(o_rows + 64) + 2 * k, w21, idesc_2n, 1);                    // O[j]
+                  umma_f16(d_even, sw_desc<true>(o_rows) + 2 * k, w0, idesc_n, 1);                           // O[j-1]
+                  umma_f16(d_odd, sw_desc<true>(e_rows + 64) + 2 * k, w21, idesc_n, 1);                      // E[j+1] x w2
+                }
+            }
+          }
+        }
+      }
+    };
+    uint32_t q = 0;                       // first-layer tiles issued so far
+    auto issue_first = [&]() {            // both first-layer tiles of one item
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t, ++q) {
+        const uint32_t st = q & 1, slot = q % 3;
+        mbar_wait(&s.in_full[st], (q >> 1) & 1);
+        tc_fence_after();
+        mbar_wait(&s.acc1_empty[slot], ((q / 3) & 1) ^ 1);
+        tc_fence_after();
+        issue_tile(in_addr + st * in_stage, w1_addr, b1_bytes, a.kb1, nk_last1, tmem_base + slot * a.acc1, a.n1,
+                   a.idesc1_n, a.idesc1_2n);
+        umma_commit_p(leader, &s.in_empty[st]);
+        umma_commit_p(leader, &s.acc1_full[slot]);
+      }
+    };
+    Eo2Iter iter(flags_l, n_items);
+    int cur = iter.take();
+    if (cur >= 0) issue_first();
+    uint32_t k = 0;                       // items whose second layer has been issued
+    while (cur >= 0) {
+      const int nxt = iter.take();
+      if (nxt >= 0) issue_first();
+      mbar_wait(&s.a3_full, k & 1);
+      tc_fence_after();
+      mbar_wait(&s.acc2_empty, (k & 1) ^ 1);
+      tc_fence_after();
+      issue_tile(a3_addr, w2_addr, b2_bytes, a.kb2, nk_last2, tmem_base + 3 * a.acc1, a.n2, a.idesc2_n, a.idesc2_2n);
+      umma_commit_p(leader, &s.a3_empty);
+      umma_commit_p(leader, &s.acc2_full);
+      ++k;
+      cur = nxt;
+    }
+  } else if (warp < 10) {
+    // ===================== mid-epilogue: first-layer accumulators -> second-layer operand tiles =====================
+    const int q4 = warp & 3;
+    const int t = (warp - 2) >> 2;                    // 0: tile A, 1: tile B
+    const int lrow = 32 * q4 + lane;
+    const float inv_scale = a.inv_scale1;
+    const int n_chunks = a.n1 >> 4;
+    Eo2Iter iter(flags_l, n_items);
+    uint32_t k = 0;
+    int item = iter.take();
+    int len_item = (item >= 0) ? __ldg(a.len0 + item / a.n_seg) : 0;
+    for (; item >= 0; ++k) {
+      const int nxt = iter.take();                                      // the next item's length is loaded a whole
+      const int len_nxt = (nxt >= 0) ? __ldg(a.len0 + nxt / a.n_seg) : 0;   // item ahead (off the critical path)
+      const int b = item / a.n_seg, sg = item - b * a.n_seg;
+      const int r = 2 * kE2Rows * sg - 1 + kBlockM * t + lrow;          // row of the intermediate activation
+      const bool valid = (r >= 0) && (r < (len_item >> a.shift1));
+      // destination: even r -> E tile row r / 2 - 127 s, odd r -> O tile row (r - 1) / 2 - 127 s + 1
+      const int eo = r & 1;
+      const int idx = ((r - eo) >> 1) - kE2Rows * sg + eo;
+      const int sw = (idx >> 1) & 3;
+      unsigned char* row0 = a3 + static_cast<size_t>(eo) * kEoTile + idx * 64;
+      const uint32_t qq = 2 * k + t, slot = qq % 3;
+      mbar_wait_relaxed(&s.acc1_full[slot], (qq / 3) & 1);
+      tc_fence_after();
+      mbar_wait_relaxed(&s.a3_empty, (k & 1) ^ 1);          // the second layer of the previous item has read the tiles
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q4) << 16) + slot * a.acc1;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t ve[16], vo[16];
+        tmem_ld_32x16(taddr + c * 16, ve);
+        tmem_ld_32x16(taddr + a.n1 + c * 16, vo);
+        tmem_ld_wait();
+        if (c == n_chunks - 1) {          // accumulator in registers: the first layer of a later item may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.acc1_empty[slot]);
+        }
+        float v[16];
+        if (valid) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s.bias1[c * 16 + c4 * 4]);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = c4 * 4 + e;
+              v[j] = fmaxf(fmaf(fmaxf(__uint_as_float(ve[j]), __uint_as_float(vo[j])), inv_scale, bv[e]), 0.f);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        __half2 hv[8], lv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hv[j] = sat_half2(v[2 * j], v[2 * j + 1]);
+          const float2 back = __half22float2(hv[j]);
+          lv[j] = __floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+        }
+        // channels 16c .. 16c+15 = K block c / 2, 16-byte chunks 2 (c & 1), 2 (c & 1) + 1; planes: hi, lo
+        unsigned char* rp = row0 + static_cast<size_t>((c >> 1) * 4) * kEoTile;
+        const int ch = 2 * (c & 1);
+        *reinterpret_cast<uint4*>(rp + (((ch) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(hv);
+        *reinterpret_cast<uint4*>(rp + (((ch + 1) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(hv + 4);
+        *reinterpret_cast<uint4*>(rp + 2 * kEoTile + (((ch) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(lv);
+        *reinterpret_cast<uint4*>(rp + 2 * kEoTile + (((ch + 1) ^ sw) << 4)) = *reinterpret_cast<const uint4*>(lv + 4);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.a3_full);
+      item = nxt;
+      len_item = len_nxt;
+    }
+  } else {
+    // ===================== epilogue: second-layer accumulators -> HBM, one output row per lane =====================
+    const int q4 = warp & 3;
+    const int eset = (warp - 10) >> 2;
+    const int lrow = 32 * q4 + lane;
+    const int row_elems = a.cout_p2 * a.out_planes;
+    const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p2 : 0;
+    const int n_chunks = a.n2 >> 4;
+    Eo2Iter iter(flags_l, n_items);
+    uint32_t k = 0;
+    int item = iter.take();
+    int len_item = (item >= 0) ? __ldg(a.len0 + item / a.n_seg) : 0;
+    for (; item >= 0; ++k) {
+      const int nxt = iter.take();
+      const int len_nxt = (nxt >= 0) ? __ldg(a.len0 + nxt / a.n_seg) : 0;
+      const int b = item / a.n_seg, sg = item - b * a.n_seg;
+      const int j = kE2Rows * sg + lrow;
+      const bool writable = (lrow < kE2Rows) && (j < a.Lp_out);
+      const bool valid = writable && (j < (len_item >> a.shift2));
+      const int64_t out_row = a.out_eo ? static_cast<int64_t>(j & 1) * a.n_pairs_out + static_cast<int64_t>(b) * a.half_lp_out + (j >> 1)
+                                       : static_cast<int64_t>(b) * a.Lp_out + j;
+      __half* orow = static_cast<__half*>(a.out) + out_row * row_elems;
+      mbar_wait_relaxed(&s.acc2_full, k & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q4) << 16) + 3 * a.acc1;
+      for (int c = eset; c < n_chunks; c += 2) {
+        uint32_t ve[16], vo[16];
+        tmem_ld_32x16(taddr + c * 16, ve);
+        tmem_ld_32x16(taddr + a.n2 + c * 16, vo);
+        tmem_ld_wait();
+        if (writable)
+          epilogue_row16(ve, vo, s.bias2 + c * 16, valid, a.inv_scale2, orow + c * 16, lo_off,
+                         a.out_f8 ? reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p2 + c * 16 : nullptr, a.cout_p2);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.acc2_empty);
+      item = nxt;
+      len_item = len_nxt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+size_t conv_eo2_smem(int n1, int n2, int kb1, int kb2) {
+  return 1024 + 2ull * kb1 * 3 * n1 * 64 + 2ull * kb2 * 3 * n2 * 64 + 2ull * kb1 * 4 * kEoTile + 1ull * kb2 * 4 * kEoTile +
+         sizeof(Eo2Smem) + 64;
+}
+
+// ------------------------------------------------------------------------------------
 // Wide layers on CTA pairs (cta_group::2, clusters of two CTAs; F16_F8 layers with streamed weights).
 //
 // One M = 256 MMA spans both SMs of a pair: each CTA stages 128 rows of A (its half of a 256-row
@@ -2533,6 +2909,54 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
     }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
   }
+  // Two consecutive even / odd layers as ONE launch (conv_eo2_kernel): the first such pair (layers 2 + 3 of the shipped
+  // network), when both are hi + lo plane layers, the accumulators fit the TMEM and everything fits shared memory.
+  if (env_int("RISER_FUSE23", 1) && m->act_planes == 2 && p->n_chunked == 0)
+    for (int i = 2; i + 1 < m->n_layers - 1; ++i) {
+      LayerPlan& l1 = p->layer[i];
+      LayerPlan& l2 = p->layer[i + 1];
+      const LayerPack& L1 = m->layer[i];
+      const LayerPack& L2 = m->layer[i + 1];
+      if (!(l1.eo && l2.eo && L1.passes == 2 && L2.passes == 2 && !L1.f8 && !L2.f8)) continue;
+      Eo2Args& e = l1.eo2;
+      std::memset(&e, 0, sizeof(e));
+      e.kb1 = (L1.cin_p + 31) / 32;
+      e.kb2 = (L2.cin_p + 31) / 32;
+      e.n1 = L1.n_tile;
+      e.n2 = L2.n_tile;
+      e.acc1 = round_up(2 * e.n1, 32);
+      e.acc2 = round_up(2 * e.n2, 32);
+      const size_t smem = conv_eo2_smem(e.n1, e.n2, e.kb1, e.kb2);
+      if (3 * e.acc1 + e.acc2 > kTmemCols || smem > static_cast<size_t>(max_smem) || e.n1 > 128 || e.n2 > 128) continue;
+      e.bias1 = L1.bias;
+      e.bias2 = L2.bias;
+      e.out = l2.args.out;
+      e.B = B;
+      e.Lp_out = l2.args.Lp_out;
+      e.n_seg = (e.Lp_out + kE2Rows - 1) / kE2Rows;
+      e.half_lp_in = l1.args.half_lp;
+      e.half_lp_out = l2.args.half_lp_out;
+      e.n_pairs_out = l2.args.n_pairs_out;
+      e.out_eo = l2.args.out_eo;
+      e.out_f8 = l2.args.out_f8;
+      e.out_planes = l2.args.out_planes;
+      e.cout_p2 = L2.cout_p;
+      e.shift1 = l1.args.shift;
+      e.shift2 = l2.args.shift;
+      e.cin_p1 = L1.cin_p;
+      e.idesc1_n = umma_idesc_f16(kBlockM, e.n1);
+      e.idesc1_2n = umma_idesc_f16(kBlockM, 2 * e.n1);
+      e.idesc2_n = umma_idesc_f16(kBlockM, e.n2);
+      e.idesc2_2n = umma_idesc_f16(kBlockM, 2 * e.n2);
+      e.inv_scale1 = L1.w_inv_scale;
+      e.inv_scale2 = L2.w_inv_scale;
+      l1.fuse_next = 1;
+      l1.eo2_smem = smem;
+      l2.fused_prev = 1;
+      RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(conv_eo2_kernel),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      break;
+    }
   // tile activity flags (ragged batches / skipped reads): one byte per M super-tile and layer
   p->activity.n_layers = 0;
   p->activity.total = 0;
@@ -2589,7 +3013,9 @@ extern "C" int riser_forward_launches(const riser_plan* p) {
   const int n = p->model->n_layers;
   const int chunks = p->n_chunked > 0 ? (p->B + p->chunk_reads - 1) / p->chunk_reads : 0;
   const int l0 = p->fuse_l0 ? (p->n_chunked > 0 ? chunks : 1) : 0;   // layer-0 launches that fusion removes
-  return chunks * p->n_chunked + (n - p->n_chunked) + 1 - l0 + (p->flags ? 1 : 0);
+  int fused = 0;
+  for (int i = 1; i < n; ++i) fused += p->layer[i].fused_prev;
+  return chunks * p->n_chunked + (n - p->n_chunked) + 1 - l0 - fused + (p->flags ? 1 : 0);
 }
 
 extern "C" int riser_plan_fused_layer0(const riser_plan* p) { return p ? p->fuse_l0 : 0; }
@@ -2600,6 +3026,7 @@ extern "C" int riser_plan_layer_eo(const riser_plan* p, int i) {
 
 extern "C" int riser_plan_layer_format(const riser_plan* p, int i) {
   if (!p || i < 1 || i >= p->model->n_layers) return 0;
+  if (p->layer[i].fused_prev) return -1;      // never materialised: computed inside the previous layer's launch
   if (p->model->layer[i].f8) return 3;
   return p->model->act_planes == 2 ? 2 : 1;
 }
@@ -2609,6 +3036,7 @@ extern "C" int riser_plan_layer_kernel(const riser_plan* p, int i) {
   if (i == 1 && p->fuse_l0 == 2) return 3;
   if (i == 1 && p->fuse_l0 == 1) return 4;
   if (p->layer[i].pair) return 2;
+  if (p->layer[i].fuse_next || p->layer[i].fused_prev) return 5;
   return p->layer[i].eo ? 1 : 0;
 }
 
@@ -2647,6 +3075,17 @@ int launch_layer0(const riser_plan* p, const float* x, int64_t ld_x, const int32
 int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const int32_t* len, int b0, int nb,
                 cudaStream_t st) {
   const LayerPlan& lp = p->layer[i];
+  if (lp.fused_prev) return RISER_OK;      // computed inside layer i - 1's launch
+  if (lp.fuse_next) {
+    RISER_REQUIRE(b0 == 0 && nb == p->B, "conv_eo2_kernel runs over the whole batch");
+    Eo2Args e = lp.eo2;
+    e.len0 = len;
+    const int n_items = e.B * e.n_seg;
+    conv_eo2_kernel<<<std::min(n_items, p->model->sm_count), kE2Threads, lp.eo2_smem, st>>>(
+        lp.tm_a, lp.tm_a8, lp.tm_b, p->layer[i + 1].tm_b, e);
+    RISER_CUDA_TRY(cudaGetLastError());
+    return RISER_OK;
+  }
   ConvArgs a = lp.args;
   a.len0 = len;
   const int fused = (i == 1 && p->fuse_l0 == 1) ? 1 : 0;

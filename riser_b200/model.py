@@ -53,13 +53,15 @@ class Plan:
         """Name of the kernel that runs conv layer i in this plan (riser_plan_layer_kernel)."""
         k = int(_lib.lib().riser_plan_layer_kernel(self._handle, i))
         return {0: "conv_tc_kernel", 1: "conv_eo_kernel", 2: "conv_pair_kernel", 3: "fused01_kernel",
-                4: "conv_tc_kernel<FUSED>"}.get(k, "?")
+                4: "conv_tc_kernel<FUSED>", 5: "conv_eo2_kernel"}.get(k, "?")
 
     def activation(self, i, n_layers, planes=None):
         """Layer i's input buffer as a [B, rows_per_read, channels] tensor (tests); `planes` = row format,
         by default the one the plan reports (layer_format)."""
         if planes is None:
             planes = self.layer_format(i) or 1
+            if planes < 0:
+                raise ValueError(f"layer {i}'s input is never materialised in this plan (fused into the previous launch)")
         off, rows, cp, c, _ = self.layer_info(i)
         dt = torch.float32 if i == n_layers else torch.float16
         nbytes = self.B * rows * cp * (4 if i == n_layers else 2)
