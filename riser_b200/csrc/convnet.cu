@@ -70,6 +70,7 @@ struct LayerPack {
   int cin = 0, cout = 0, cin_p = 0, cout_p = 0, n_tile = 0, n_tiles = 0;
   __half* w = nullptr;    // [passes][3][cout_p][cin_p] fp16 (layers >= 1)
   uint8_t* w8 = nullptr;  // F16_F8 mode: [3][cout_p][2*cin_p] e4m3 = [W_lo | W_hi * 2^-9] (correction pass)
+  __half* wkc = nullptr;  // layer 1, F16_X3 terms concatenated along K: [3][cout_p][64] = [W_hi | W_hi | W_lo | 0] (fused01 MODE 4)
   float* w0 = nullptr;    // layer 0 only: fp32 [cout][3]
   float* bias = nullptr;  // fp32 [cout_p], zero padded
   int passes = 1;           // fp16 weight planes of this layer (hi [, lo])
@@ -167,6 +168,7 @@ struct LayerPlan {
   CUtensorMap tm_bl, tm_b8l;              // conv_pair_kernel: weight maps whose box is half of the LAST N tile
   int eo = 0;                             // input in the even / odd plane layout -> conv_eo_kernel
   int pair = 0;                           // CTA pairs (cta_group::2) -> conv_pair_kernel
+  int kc = 0;                             // fused01_kernel<4>: layer 1's hi / lo terms concatenated along K
   int fuse_next = 0;                      // this layer and the next one run as ONE conv_eo2_kernel launch
   int fused_prev = 0;                     // computed inside the previous layer's launch: its input buffer is never written
   Eo2Args eo2;                            // fuse_next: arguments of the two-layer launch
@@ -983,16 +985,23 @@ struct F2Iter {
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
 // MODE: 0 = F16, 1 = F16_W2 (weights hi + lo), 2 = F16_X3 (weights and activations hi + lo),
-// 3 = F16_F8 (fp16 pass + e4m3 correction pass: second tile of a stage / second weight set are bytes)
+// 3 = F16_F8 (fp16 pass + e4m3 correction pass: second tile of a stage / second weight set are bytes),
+// 4 = F16_X3 with the three terms CONCATENATED ALONG K ("KC"; layer 0 with <= 20 output channels): a layer-1 operand
+//     row is [a_hi (20 ch) | a_lo (20) | a_hi (20) | 0 (4)] = 64 channels = one 128-byte SWIZZLE_128B row, the weight
+//     row [W_hi | W_hi | W_lo | 0], so a tap costs 4 K steps instead of 3 x 2 (the 32-channel blocks of the plane
+//     layout are 37 % zero padding); and E[j] x [w1; w0], O[j] x [w2; w1] feed both conv positions at once (N = 64).
+//     The launch is bound by the tensor cores' operand reads from shared memory (81 % of that pipe's peak in the
+//     plane layout, where an item was 76 MMAs of >= 45.5 cycles): 36 MMAs per item here.
 template <int MODE>
 __global__ void __launch_bounds__(kF2Threads, 1)
 fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b8, const ConvArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   constexpr bool F8 = (MODE == 3);
+  constexpr bool KC = (MODE == 4);
   constexpr int PLANES = (MODE >= 2) ? 2 : 1;
   constexpr int WPLANES = (MODE == 1 || MODE == 2) ? 2 : 1;
-  constexpr uint32_t kW1Bytes = (F8 ? 2 : WPLANES) * 3 * 32 * 64;
+  constexpr uint32_t kW1Bytes = KC ? 3 * 32 * 128 : (F8 ? 2 : WPLANES) * 3 * 32 * 64;
   constexpr uint32_t kB0Bytes = kF2N0 * 64;
   constexpr uint32_t kA1Stage = PLANES * 2 * kF2A1Tile;
   unsigned char* w1 = base;
@@ -1078,9 +1087,13 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       mbar_arrive_expect_tx(&s.w_full, kW1Bytes);
       // taps are stored in REVERSE order (slot 2 - tap): [w2; w1] and [w1; w0] are then contiguous 64-row B
       // operands, so one N = 64 MMA feeds the even and the odd conv position from the same A rows
-      for (int wp = 0; wp < WPLANES; ++wp)
-        for (int tap = 0; tap < 3; ++tap)
-          tma_load_2d(w1 + (wp * 3 + 2 - tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+      if (KC) {      // tm_b = the K-concatenated layer-1 weights [tap][32 rows][64 channels], 4 KB per tap
+        for (int tap = 0; tap < 3; ++tap) tma_load_2d(w1 + (2 - tap) * 4096, &tm_b, &s.w_full, 0, tap * a.cout_p);
+      } else {
+        for (int wp = 0; wp < WPLANES; ++wp)
+          for (int tap = 0; tap < 3; ++tap)
+            tma_load_2d(w1 + (wp * 3 + 2 - tap) * 2048, &tm_b, &s.w_full, 0, (wp * 3 + tap) * a.cout_p);
+      }
       if (F8)
         for (int tap = 0; tap < 3; ++tap)
           tma_load_2d(w1 + (3 + 2 - tap) * 2048, &tm_b8, &s.w_full, 0, tap * a.cout_p);
@@ -1196,11 +1209,33 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
             }
           }
         };
+        if (KC) {
+          // one 64-channel K block per tap set: 4 K steps x 4 MMAs per sub-tile (E tile at a1s, O tile behind it;
+          // rows of 128 bytes; weight slots [w2; w1; w0] of 4 KB)
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t w21 = sw_desc<false>(w1_addr) + 2 * k;
+              const uint64_t w10 = sw_desc<false>(w1_addr + 4096) + 2 * k;
+              const uint64_t w0 = sw_desc<false>(w1_addr + 8192) + 2 * k;
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t e_rows = a1s + sub * 128 * 128, o_rows = e_rows + 2 * kF2A1Tile;
+                const uint32_t d_even = tmem_base + st * 128 + 2 * sub * 32, d_odd = d_even + 32;
+                umma_f16(d_even, sw_desc<false>(e_rows) + 2 * k, w10, idesc64, k != 0);      // E[j]   -> (even | odd)
+                umma_f16(d_even, sw_desc<false>(o_rows + 128) + 2 * k, w21, idesc64, 1);     // O[j]   -> (even | odd)
+                umma_f16(d_even, sw_desc<false>(o_rows) + 2 * k, w0, a.idesc, 1);            // O[j-1] -> even
+                umma_f16(d_odd, sw_desc<false>(e_rows + 128) + 2 * k, w21, a.idesc, 1);      // E[j+1] x w2 -> odd
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int wp = 0; wp < WPLANES; ++wp)
 #pragma unroll
           for (int ap = 0; ap < ((wp == 0 && !F8) ? PLANES : 1); ++ap)
             issue_group(a1s + ap * 2 * kF2A1Tile, w1_addr + wp * 3 * 2048, false, wp == 0 && ap == 0);
+        }
         if (F8)   // correction pass: [a8 | lo8] x [W_lo | W_hi * 2^-9], 64 e4m3 per row = 2 k-steps
           issue_group(a1s + 2 * kF2A1Tile, w1_addr + 3 * 2048, true, false);
         umma_commit_p(leader, &s.a1_empty[st]);
@@ -1335,10 +1370,27 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
         __half2 hv[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) hv[j] = sat_half2(v[2 * j], v[2 * j + 1]);
+        if (KC) {
+          // 128-byte row [hi ch 0..19 | lo ch 0..19 | hi ch 0..19 | 0]: 32 words = hv[0..9], lv[0..9], hv[0..9], 0, 0
+          uint32_t w[32];
 #pragma unroll
-        for (int c8 = 0; c8 < 3; ++c8)
-          *reinterpret_cast<uint4*>(rp + ((c8 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(hv + 4 * c8);
-        if (PLANES == 2 && !F8) {
+          for (int j = 0; j < 10; ++j) {
+            const float2 back = __half22float2(hv[j]);
+            w[j] = w[20 + j] = h2_bits(hv[j]);
+            w[10 + j] = h2_bits(__floats2half2_rn(v[2 * j] - back.x, v[2 * j + 1] - back.y));
+          }
+          w[30] = w[31] = 0u;
+          unsigned char* rk = a1_ring + st * kA1Stage + h * 2 * kF2A1Tile + row * 128;
+          const int swk = row & 7;                        // SWIZZLE_128B: 16-byte chunk c at c ^ (row & 7)
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(rk + ((c8 ^ swk) << 4)) = make_uint4(w[4 * c8], w[4 * c8 + 1], w[4 * c8 + 2], w[4 * c8 + 3]);
+        } else {
+#pragma unroll
+          for (int c8 = 0; c8 < 3; ++c8)
+            *reinterpret_cast<uint4*>(rp + ((c8 ^ sw) << 4)) = *reinterpret_cast<const uint4*>(hv + 4 * c8);
+        }
+        if (PLANES == 2 && !F8 && !KC) {
           __half2 lv[12];
 #pragma unroll
           for (int j = 0; j < 12; ++j) {
@@ -1469,6 +1521,7 @@ FusedKernelFn pick_fused01(int mode) {
   if (mode == 0) return fused01_kernel<0>;
   if (mode == 1) return fused01_kernel<1>;
   if (mode == 2) return fused01_kernel<2>;
+  if (mode == 4) return fused01_kernel<4>;
   return fused01_kernel<3>;
 }
 size_t fused01_smem(int planes, int wplanes) {
@@ -2153,15 +2206,32 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   //  is narrower than the others -- every pair then still gets its share of both widths)
   auto item_super = [&](int item) { return a.super0 + item / a.n_tiles; };
   auto item_n = [&](int item) { return (item % a.n_tiles + item / a.n_tiles) % a.n_tiles; };
-  auto active = [&](int item) { return !a.flags || __ldg(a.flags + item_super(item)) != 0; };
+  // Activity flag of item, item + stride, ...: the NEXT item's flag is loaded while the current item is worked on
+  // (a global load per item otherwise sits on the critical path of the single-thread roles).
+  struct PairFlags {
+    const uint8_t* flags;
+    int n_tiles, super0, stride, n_items;
+    uint32_t next;
+    __device__ __forceinline__ uint32_t load(int item) const {
+      return (flags && item < n_items) ? __ldg(flags + super0 + item / n_tiles) : 1u;
+    }
+    __device__ __forceinline__ PairFlags(const uint8_t* f, int nt, int s0, int first, int stride_, int n)
+        : flags(f), n_tiles(nt), super0(s0), stride(stride_), n_items(n) { next = load(first); }
+    __device__ __forceinline__ bool take(int item) {      // call once per item, in order
+      const uint32_t now = next;
+      next = load(item + stride);
+      return now != 0;
+    }
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
       for (int item = pair; item < n_items; item += n_pairs_grid) {
-        if (!active(item)) continue;
+        if (!fl.take(item)) continue;
         const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM - 1;
         const int n_idx = item_n(item);
         const bool last_n = (n_idx == a.n_tiles - 1);
@@ -2221,8 +2291,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int nk_last = (a.cin_p - (a.kb16 - 1) * 64) / 16;
       const int nk_last8 = (2 * a.cin_p - (a.k_blocks - a.kb16 - 1) * 128) / 32;
       const uint32_t acc_stride = MS * a.acc_cols;
+      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
       for (int item = pair; item < n_items; item += n_pairs_grid) {
-        if (!active(item)) continue;
+        if (!fl.take(item)) continue;
         const uint32_t d_base = tmem_base + stage * acc_stride;
         const uint32_t idesc = (item_n(item) == a.n_tiles - 1) ? a.idesc_last : a.idesc;
         for (int kb = 0; kb < a.k_blocks; ++kb) {
@@ -2283,8 +2354,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
     int stage = 0, it = -1;
     uint32_t acc_phase = 0;
+    PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
     for (int item = pair; item < n_items; item += n_pairs_grid) {
-      if (!active(item)) continue;
+      if (!fl.take(item)) continue;
       ++it;
       const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM;
       const int n_idx = item_n(item);
@@ -2629,6 +2701,21 @@ extern "C" int riser_model_create(riser_model** out, int n_layers, const int* ch
       }
       RISER_CUDA_TRY(cudaMalloc(&L.w, sizeof(__half) * w.size()));
       RISER_CUDA_TRY(cudaMemcpy(L.w, w.data(), sizeof(__half) * w.size(), cudaMemcpyHostToDevice));
+      if (i == 1 && L.passes == 2 && m->act_planes == 2 && !L.f8 && L.cin <= 20 && (L.cin & 1) == 0 && L.cout_p == 32) {
+        // K-concatenated operand of fused01_kernel<4>: input channel ci at k = ci (x a_hi), 20 + ci (x a_lo), 40 + ci (x a_hi)
+        std::vector<__half> kc(static_cast<size_t>(3) * L.cout_p * 64, __float2half(0.f));
+        for (int tap = 0; tap < 3; ++tap)
+          for (int co = 0; co < L.cout; ++co)
+            for (int ci = 0; ci < L.cin; ++ci) {
+              const size_t idx = (static_cast<size_t>(tap) * L.cout_p + co) * L.cin_p + ci;
+              __half* row = kc.data() + (static_cast<size_t>(tap) * L.cout_p + co) * 64;
+              row[ci] = w[idx];
+              row[20 + ci] = w[idx];
+              row[40 + ci] = w[per_pass + idx];
+            }
+        RISER_CUDA_TRY(cudaMalloc(&L.wkc, sizeof(__half) * kc.size()));
+        RISER_CUDA_TRY(cudaMemcpy(L.wkc, kc.data(), sizeof(__half) * kc.size(), cudaMemcpyHostToDevice));
+      }
     }
     cin = L.cout;
     cin_p = L.cout_p;
@@ -2647,6 +2734,7 @@ extern "C" int riser_model_destroy(riser_model* m) {
   for (int i = 0; i < m->n_layers; ++i) {
     cudaFree(m->layer[i].w);
     cudaFree(m->layer[i].w8);
+    cudaFree(m->layer[i].wkc);
     cudaFree(m->layer[i].w0);
     cudaFree(m->layer[i].bias);
   }
@@ -2855,6 +2943,11 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.rows_per_super = 2 * kF2Pairs;
       lp.smem = fused01_smem(m->act_planes, L.f8 ? 2 : L.passes);
       a.planes = m->act_planes;     // fused01_kernel's own modes (see pick_fused01)
+      if (L.wkc && m->layer[0].cout <= 20 && env_int("RISER_KC", 1)) {
+        lp.kc = 1;      // the three hi / lo terms concatenated along K (fused01_kernel<4>); same shared-memory footprint
+        const int st3 = make_tmap(&lp.tm_b, L.wkc, 64, 3ull * L.cout_p, 32, false);
+        if (st3) return st3;
+      }
     }
     if (lp.eo) {
       // conv_eo_kernel: E plane = rows [0, n_pairs), O plane = rows [n_pairs, 2 n_pairs) of the same buffer
@@ -2990,7 +3083,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
   for (int ms = 1; ms <= 2; ++ms)
     RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_conv_pair(ms)),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  for (int pl = 0; pl < 4; ++pl)
+  for (int pl = 0; pl < 5; ++pl)
     RISER_CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_fused01(pl)),
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   for (int k32v = 0; k32v < 2; ++k32v)
@@ -3105,7 +3198,7 @@ int launch_conv(const riser_plan* p, int i, const float* x, int64_t ld_x, const 
     if ((a.n_supers + grid - 1) / grid > kF2MaxLocalItems) a.flags = nullptr;   // (every item treated as active)
     RISER_REQUIRE((ld_x & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                   "riser_forward: x must be 16-byte aligned with ld_x a multiple of 4 (bulk copies of the signal)");
-    pick_fused01(a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(
+    pick_fused01(lp.kc ? 4 : a.f8 ? 3 : (a.planes == 2 ? 2 : (a.wplanes == 2 ? 1 : 0)))<<<grid, kF2Threads, lp.smem, st>>>(
         lp.tm_b, lp.tm_b8, a);
     RISER_CUDA_TRY(cudaGetLastError());
     return RISER_OK;

@@ -55,7 +55,8 @@ def oracle_layers(state, x):
                                             (2, (PREC_F16_X3, "flat")), (0, (PREC_F16, "flat")),
                                             (2, (PREC_F16_F8, "nopair")), (2, (PREC_F16_F8, "pair2")), (2, (PREC_F16_F8, "pair5")),
                                             (2, (PREC_F16_F8, "pair192")), (2, (PREC_F16_F8, 6)),
-                                            (2, (PREC_F16_F8, "nofuse23")), (2, (PREC_F16_X3, "nofuse23"))])
+                                            (2, (PREC_F16_F8, "nofuse23")), (2, (PREC_F16_X3, "nofuse23")),
+                                            (2, (PREC_F16_X3, "nokc")), (2, (PREC_F16_F8, "nokc"))])
 def test_every_layer_against_oracle(fuse, precision, monkeypatch):
     monkeypatch.setenv("RISER_FUSE_L0", str(fuse))
     if isinstance(precision, tuple) and precision[1] == "flat":     # without the even / odd plane layout
@@ -72,6 +73,9 @@ def test_every_layer_against_oracle(fuse, precision, monkeypatch):
         monkeypatch.setenv("RISER_PAIR_FROM", "5")
         monkeypatch.setenv("RISER_PAIR_MS", "2")
         monkeypatch.setenv("RISER_DUAL_ISSUE", "0")
+    elif isinstance(precision, tuple) and precision[1] == "nokc":      # layer 1's hi / lo terms as three plane passes
+        precision = precision[0]                                        # (fused01_kernel<2>) instead of one K = 64 pass
+        monkeypatch.setenv("RISER_KC", "0")
     elif isinstance(precision, tuple) and precision[1] == "nofuse23":  # layers 2 and 3 as two conv_eo_kernel launches
         precision = precision[0]
         monkeypatch.setenv("RISER_FUSE23", "0")
