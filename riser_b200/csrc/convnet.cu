@@ -2158,7 +2158,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t b_bytes = (a.n_tile / 2) * 128;           // this CTA's half of a (full-width) weight tile
   unsigned char* a_ring = base;
   unsigned char* b_region = base + static_cast<size_t>(a.a_stages) * kAGroup;
-  ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + static_cast<size_t>(a.b_stages) * b_bytes);
+  // (`resident`: one N tile whose halves fit -- every CTA keeps ITS half of all taps and K blocks for the whole kernel,
+  //  [tap][K block][n_tile / 2 rows x 128 B], and nothing but activations is streamed: layer 5)
+  const size_t b_region_bytes = a.resident ? static_cast<size_t>(3) * a.k_blocks * b_bytes : static_cast<size_t>(a.b_stages) * b_bytes;
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(b_region + b_region_bytes);
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -2183,6 +2186,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(&s.b_full[i], 1);
       mbar_init(&s.b_empty[i], n_issuers);
     }
+    mbar_init(&s.w_full, 1);
     for (int i = 0; i < a.acc_stages; ++i) {
       for (int ms = 0; ms < MS; ++ms) {
         mbar_init(&s.tmem_full_ms[i][ms], 1);
@@ -2227,6 +2231,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
+      if (a.resident) {      // both CTAs' halves complete on the leader's barrier (the issuer lives there)
+        if (leader) mbar_arrive_expect_tx(&s.w_full, 2u * static_cast<uint32_t>(b_region_bytes));
+        const int n0 = static_cast<int>(rank) * (a.n_tile / 2);
+        for (int tap = 0; tap < 3; ++tap)
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            unsigned char* dst = b_region + static_cast<size_t>(tap * a.k_blocks + kb) * b_bytes;
+            if (kb >= a.kb16) tma_load_2d_pair(dst, &tm_b8, &s.w_full, (kb - a.kb16) * 128, tap * a.cout_p + n0);
+            else tma_load_2d_pair(dst, &tm_b, &s.w_full, kb * 64, tap * a.cout_p + n0);
+          }
+      }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
@@ -2258,6 +2272,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
+            if (a.resident) break;
             mbar_wait(&s.b_empty[sb], pb ^ 1);
             if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_tx);
             if (is8)
@@ -2291,6 +2306,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int nk_last = (a.cin_p - (a.kb16 - 1) * 64) / 16;
       const int nk_last8 = (2 * a.cin_p - (a.k_blocks - a.kb16 - 1) * 128) / 32;
       const uint32_t acc_stride = MS * a.acc_cols;
+      if (a.resident) {
+        mbar_wait(&s.w_full, 0);
+        tc_fence_after();
+      }
       PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
       for (int item = pair; item < n_items; item += n_pairs_grid) {
         if (!fl.take(item)) continue;
@@ -2304,9 +2323,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t a_addr = a_ring_addr + sa * kAGroup;
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
-            mbar_wait(&s.b_full[sb], pb);
-            tc_fence_after();
-            const uint64_t db = sw_desc<false>(b_region_addr + sb * b_bytes);
+            if (!a.resident) {
+              mbar_wait(&s.b_full[sb], pb);
+              tc_fence_after();
+            }
+            const uint64_t db = sw_desc<false>(a.resident ? b_region_addr + (tap * a.k_blocks + kb) * b_bytes
+                                                          : b_region_addr + sb * b_bytes);
 #pragma unroll
             for (int ms = 0; ms < MS; ++ms) {
               if (ms < ms_lo || ms >= ms_hi) continue;      // (the other issuer's sub-tile)
@@ -2322,10 +2344,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   else umma_f16_pair_p(lead, d_base + ms * a.acc_cols, da + 2 * k, db + 2 * k, idesc, (kb | tap | k) != 0);
                 }
             }
-            umma_commit_pair_p(lead, &s.b_empty[sb]);
-            if (++sb == a.b_stages) {
-              sb = 0;
-              pb ^= 1;
+            if (!a.resident) {
+              umma_commit_pair_p(lead, &s.b_empty[sb]);
+              if (++sb == a.b_stages) {
+                sb = 0;
+                pb ^= 1;
+              }
             }
           }
           umma_commit_pair_p(lead, &s.a_empty[sa]);
@@ -2968,7 +2992,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.rows_per_super = a.ms * 2 * kBlockM;
     }
     if (L.f8 && !a.resident && !k32 && !lp.eo && (L.n_tile % 16) == 0 && env_int("RISER_PAIR", 1) &&
-        i >= env_int("RISER_PAIR_FROM", 6)) {
+        (i >= env_int("RISER_PAIR_FROM", 6) ||
+         (L.n_tiles == 1 && static_cast<size_t>(3) * a.k_blocks * (L.cout_p / 2) * 128 + 3 * 136 * 128 <= avail &&
+          env_int("RISER_PAIR_RESIDENT", 1)))) {
       // conv_pair_kernel: M = 256 over two CTAs, each holds 128 rows of A and half of every weight tile
       // N tiles of the pair kernel: 256 wide (the widest M = 256 MMA: fewest shared-memory operand bytes per MAC)
       // with ONE narrower last tile instead of equal tiles -- cout_p itself (the next layer's K) is unchanged
@@ -2996,8 +3022,16 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b_stages = std::max(2, std::min<int>(kMaxBStages, static_cast<int>((avail - a.a_stages * a_group) / half_b)));
       a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
       a.dual = (a.ms == 2 && env_int("RISER_DUAL_ISSUE", 1)) ? 1 : 0;
+      a.resident = 0;
+      size_t b_total = a.b_stages * half_b;
+      const size_t w_half = static_cast<size_t>(3) * a.k_blocks * half_b;      // this CTA's half of every tap and K block
+      if (a.n_tiles == 1 && w_half + 3 * a_group <= avail && env_int("RISER_PAIR_RESIDENT", 1)) {
+        a.resident = 1;
+        a.a_stages = std::min<int>(kMaxAStages, static_cast<int>((avail - w_half) / a_group));
+        b_total = w_half;
+      }
       a.epi_sets = 4;
-      lp.smem = fixed + a.a_stages * a_group + a.b_stages * half_b;
+      lp.smem = fixed + a.a_stages * a_group + b_total;
       lp.rows_per_super = a.ms * 256;
     }
     lp.n_supers_total = (rows_in + lp.rows_per_super - 1) / lp.rows_per_super;
