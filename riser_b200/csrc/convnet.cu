@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -2999,7 +3000,9 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       // N tiles of the pair kernel: 256 wide (the widest M = 256 MMA: fewest shared-memory operand bytes per MAC)
       // with ONE narrower last tile instead of equal tiles -- cout_p itself (the next layer's K) is unchanged
       lp.pair = 1;
-      const int wide = std::max(64, std::min(kMaxNTile, env_int("RISER_PAIR_NTILE", kMaxNTile)) & ~31);
+      char ntile_key[32];
+      snprintf(ntile_key, sizeof ntile_key, "RISER_PAIR_NTILE_L%d", i);      // per-layer override (tuning)
+      const int wide = std::max(64, std::min(kMaxNTile, env_int(ntile_key, env_int("RISER_PAIR_NTILE", kMaxNTile))) & ~31);
       a.n_tile = std::min(wide, L.cout_p);
       a.n_tiles = (L.cout_p + a.n_tile - 1) / a.n_tile;
       a.n_last = L.cout_p - (a.n_tiles - 1) * a.n_tile;

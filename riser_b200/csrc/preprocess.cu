@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace riser {
 namespace {
@@ -23,6 +24,8 @@ constexpr int kBinsPerThread = kBins / kThreads;
 constexpr int kSubBins = 128;           // refinement pass (shift <= 7)
 constexpr int kMaxLen = 98304;          // samples staged in smem (192 KB)
 constexpr int kMaxRuns = 512;           // outlier-run start indices collected per read (more: rescan path)
+
+constexpr int kDefaultF64 = 0;            // samples per group of four on the float64 pipe (RISER_NORM_F64)
 
 constexpr double kOutlierLimit = 3.5;   // riser/preprocess.py:6
 constexpr double kScalingFactor = 1.4826;  // riser/preprocess.py:7
@@ -63,39 +66,40 @@ struct StagedWindow {
   int a, n;
   __device__ __forceinline__ int operator[](int i) const { return stage[a + i]; }
   template <class F>
-  __device__ __forceinline__ void chunk(int c, int end, F& f) const {
+  __device__ __forceinline__ void full_chunk(int c, F& f) const {      // all 8 samples of chunk c lie in the window
     const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    const int base = 8 * c;
-    if (base >= a && base + 8 <= end) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f(static_cast<int>(static_cast<int16_t>(w[j] & 0xffffu)));
-        f(static_cast<int>(static_cast<int16_t>(w[j] >> 16)));
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int p = base + j;
-        if (p >= a && p < end) f(static_cast<int>(static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu)));
-      }
+    for (int j = 0; j < 4; ++j) {
+      f(static_cast<int>(static_cast<int16_t>(w[j] & 0xffffu)));
+      f(static_cast<int>(w[j]) >> 16);
     }
   }
-  // Chunk order: warp w owns the contiguous chunks [w R, (w + 1) R); lane l walks l S .. l S + S - 1 of them with
+  // Chunk order: warp w owns the contiguous full chunks [w R, (w + 1) R); lane l walks l S .. l S + S - 1 of them with
   // S odd, so the 16-byte loads of a warp stay bank-conflict free while its lanes work on samples ~8 S apart --
   // neighbouring samples of a squiggle sit on the same current level, and 32 lanes hitting the same few histogram
-  // bins serialise the shared-memory atomics.  The (< 64) chunks left over per warp are taken lane by lane.
+  // bins serialise the shared-memory atomics.  The (< 64) chunks left over per warp are taken lane by lane.  The
+  // (< 8) samples before the first and after the last full chunk are taken one per thread by threads 0..15, so the
+  // chunk loop carries no edge tests.
   template <class F>
   __device__ __forceinline__ void for_each(F f) const {
     const int end = a + n;
-    const int n_chunks = (end + 7) >> 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int R = (n_chunks + kWarps - 1) / kWarps;
-    const int c0 = warp * R, c1 = min(c0 + R, n_chunks);
+    const int c_first = (a + 7) >> 3, c_last = end >> 3;        // full chunks: [c_first, c_last) (may be empty)
+    const int head_end = min(end, 8 * c_first);                 // head samples: positions [a, head_end)
+    const int tail_start = max(8 * c_last, head_end);           // tail samples: positions [tail_start, end)
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+      const int pos = (tid < 8) ? a + tid : tail_start + tid - 8;
+      if (pos < ((tid < 8) ? head_end : end)) f(static_cast<int>(stage[pos]));
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_full = max(c_last - c_first, 0);
+    const int R = (n_full + kWarps - 1) / kWarps;
+    const int c0 = c_first + warp * R, c1 = min(c0 + R, c_first + n_full);
     int S = (c1 - c0) >> 5;
     S = (S > 0) ? ((S - 1) | 1) : 0;          // largest odd number <= (c1 - c0) / 32
-    for (int i = 0; i < S; ++i) chunk(c0 + lane * S + i, end, f);
-    for (int c = c0 + 32 * S + lane; c < c1; c += 32) chunk(c, end, f);
+    for (int i = 0; i < S; ++i) full_chunk(c0 + lane * S + i, f);
+    for (int c = c0 + 32 * S + lane; c < c1; c += 32) full_chunk(c, f);
   }
 };
 
@@ -105,17 +109,14 @@ struct StagedWindow {
 // low bits inside the located bin.  Block-uniform control flow; all threads get r1, r2.
 template <class KeyFn>
 __device__ int select_two(KeyFn key, const StagedWindow& win, uint32_t maxkey, uint32_t k1, uint32_t k2,
-                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false, int dbg = 0) {
+                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false) {
   const int tid = threadIdx.x;
   int shift = 0;
   while ((maxkey >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
-  for (int i = tid; i < kBins; i += kThreads) s.hist[i] = 0;
+  for (int i = tid; i < kBins / 4; i += kThreads) reinterpret_cast<uint4*>(s.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  if (dbg & 2) {          // timing experiment: loads and keys, no atomics
-    uint32_t acc = 0;
-    win.for_each([&](int e) { acc += key(e) >> shift; });
-    if (acc == 0x12345678u) s.hist[0] = acc;
-    if (tid == 0) s.hist[maxkey >> (shift + 1)] = win.n;
+  if (shift == 0) {       // (every real squiggle window: no shift instruction per sample)
+    win.for_each([&](int e) { atomicAdd(&s.hist[key(e)], 1u); });
   } else {
     win.for_each([&](int e) { atomicAdd(&s.hist[key(e) >> shift], 1u); });
   }
@@ -321,7 +322,7 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     uint32_t r1, r2;
     const int range = vmax - vmin;
     const int shift_used = select_two([&](int e) { return static_cast<uint32_t>(e - vmin); }, x,
-                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true, dbg);
+                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true);
     const int med2 = 2 * vmin + static_cast<int>(r1 + r2);
 
     // ---- MAD on keys d = |2x - med2| = 2|x - median| -> mad4 = 4 * MAD (exact)
@@ -380,7 +381,8 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       const double Dd = __dmul_rn(2.0, denom);
       const double yrcp = __ddiv_rn(1.0, Dd);
       auto quot = [&](int ki) {
-        const double k = static_cast<double>(ki);
+        // (double) ki without an I2F: 2^52 + 2^31 + ki has ki ^ 0x80000000 in its low word; one exact DADD removes the offset
+        const double k = __dadd_rn(__hiloint2double(0x43300000, ki ^ static_cast<int>(0x80000000u)), -4503601774854144.0);
         const double q0 = __dmul_rn(k, yrcp);
         const double e = __fma_rn(-q0, Dd, k);
         return __fma_rn(e, yrcp, q0);
@@ -389,7 +391,8 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       // and the float64 pipe is what bounds this kernel: when the value range fits the histogram, the fp32 result
       // of every VALUE is tabulated once (in the histogram's storage, free after the MAD search) and the per-sample
       // work becomes one shared-memory look-up.
-      const bool use_lut = (shift_used == 0) && !(dbg & 8);
+      const int n_f64 = dbg & 7;            // samples of every group of four whose quotient is computed, not looked up
+      const bool use_lut = (shift_used == 0) && n_f64 < 4;
       float* lut = reinterpret_cast<float*>(s.hist);
       if (use_lut)
         for (int u = tid; u <= range; u += kThreads) lut[u] = static_cast<float>(quot(2 * (vmin + u) - med2));
@@ -445,10 +448,11 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
         }
       };
 
-      // ---- normalise: 4 samples per thread and step (two 8-byte shared loads realigned by the window's
-      //      phase), 16-byte stores; outlier-run starts are pushed to s.runs
+      // ---- normalise: 4 samples per thread and step, 16-byte stores; outlier-run starts are pushed to s.runs.
+      //      The window's phase inside its 8-byte staging words (sh = a & 3, block-uniform) selects one of four
+      //      specialised loops: at most two shared loads and two funnel shifts per group, running pointers, no
+      //      per-group address arithmetic (the loop is issue-bound: 87 -> ~30 instructions per group).
       const int sh = a & 3;
-      const int16_t* q8 = stage + (a & ~3);
       // |2x - med2| > dthr  <=>  x > x_hi or x < x_lo (clamped to int16: beyond the type nothing can exceed);
       // tested for the group's four samples at once on the packed 16-bit halves
       const int x_hi = min(32767, (med2 + static_cast<int>(dthr)) >> 1);            // floor
@@ -474,55 +478,84 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
           }
         }
       };
-      auto group_loop = [&](auto value_of) {
-        uint32_t gmask = 0;
-        int step = 0;
-        for (int gidx = tid; gidx < ((dbg & 4) ? 0 : n_groups); gidx += kThreads, ++step) {
-          const int i0 = 4 * gidx;
-          const uint2 lo = *reinterpret_cast<const uint2*>(q8 + i0);
-          const uint2 hi = *reinterpret_cast<const uint2*>(q8 + i0 + 4);
-          const uint32_t wa = (sh & 2) ? lo.y : lo.x, wb = (sh & 2) ? hi.x : lo.y, wc = (sh & 2) ? hi.y : hi.x;
-          const uint32_t p0 = __funnelshift_r(wa, wb, 16 * (sh & 1)), p1 = __funnelshift_r(wb, wc, 16 * (sh & 1));
-          const int xs[4] = {static_cast<int16_t>(p0 & 0xffffu), static_cast<int16_t>(p0 >> 16),
-                             static_cast<int16_t>(p1 & 0xffffu), static_cast<int16_t>(p1 >> 16)};
-          const int cnt = min(4, n - i0);
-          if (cnt == 4) {
-            float4 v;
-            v.x = value_of(xs[0], 0);
-            v.y = value_of(xs[1], 1);
-            v.z = value_of(xs[2], 2);
-            v.w = value_of(xs[3], 3);
-            if (dbg & 1) {
-              if (v.x == 123.456f) o[i0] = v.y + v.z + v.w;
+      const int n_full = n >> 2;                       // groups of four whole samples
+      auto group_loop = [&](auto sh_const, auto nf_const, auto value_of, auto value_of_x4, auto f64_x4) {
+        constexpr int SH = decltype(sh_const)::value;
+        constexpr int NF = decltype(nf_const)::value;
+        // group g = samples 4g .. 4g + 3 = 16-bit halves SH .. SH + 3 of the staging words wbase[2g ..]
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (a & ~3)) + 2 * tid;
+        float4* op = reinterpret_cast<float4*>(o) + tid;
+        for (int g0 = 0; g0 < n_full; g0 += 32 * kThreads) {       // 32 steps (32,768 samples) per mask word
+          uint32_t gmask = 0, bit = 1;
+          const int g1 = min(n_full, g0 + 32 * kThreads);
+#pragma unroll 2
+          for (int g = g0 + tid; g < g1; g += kThreads, wp += 2 * kThreads, op += kThreads, bit <<= 1) {
+            uint32_t p0, p1;
+            if (SH == 0) {
+              const uint2 v = *reinterpret_cast<const uint2*>(wp);
+              p0 = v.x;
+              p1 = v.y;
+            } else if (SH == 1) {
+              const uint2 v = *reinterpret_cast<const uint2*>(wp);
+              const uint32_t c = wp[2];
+              p0 = __funnelshift_r(v.x, v.y, 16);
+              p1 = __funnelshift_r(v.y, c, 16);
+            } else if (SH == 2) {
+              p0 = wp[1];
+              p1 = wp[2];
             } else {
-              *reinterpret_cast<float4*>(o + i0) = v;
+              const uint32_t c = wp[1];
+              const uint2 v = *reinterpret_cast<const uint2*>(wp + 2);
+              p0 = __funnelshift_r(c, v.x, 16);
+              p1 = __funnelshift_r(v.x, v.y, 16);
             }
-          } else {       // tail group: what lies past the window in the staging buffer is not a sample
-            for (int e = 0; e < cnt; ++e) o[i0 + e] = value_of(xs[e], 0);
+            float4 v;      // value_of_x4(p): the value of a sample given 4 * sample; NF of the four on the float64 pipe
+            v.x = (NF >= 4) ? f64_x4(static_cast<int>(p0 << 16) >> 14) : value_of_x4(static_cast<int>(p0 << 16) >> 14);
+            v.y = (NF >= 2) ? f64_x4(static_cast<int>(p0 & 0xffff0000u) >> 14) : value_of_x4(static_cast<int>(p0 & 0xffff0000u) >> 14);
+            v.z = (NF >= 3) ? f64_x4(static_cast<int>(p1 << 16) >> 14) : value_of_x4(static_cast<int>(p1 << 16) >> 14);
+            v.w = (NF >= 1) ? f64_x4(static_cast<int>(p1 & 0xffff0000u) >> 14) : value_of_x4(static_cast<int>(p1 & 0xffff0000u) >> 14);
+            *op = v;
+            // some sample of this group is an outlier
+            if (__vimax3_s16x2(p0, p1, hi2) != hi2 || __vimin3_s16x2(p0, p1, lo2) != lo2) gmask |= bit;
           }
-          // some sample of this group is an outlier (or, in the tail group, stale data past the window)
-          const bool hit = !(dbg & 32) && (__vimax3_s16x2(p0, p1, hi2) != hi2 || __vimin3_s16x2(p0, p1, lo2) != lo2);
-          gmask |= (hit ? 1u : 0u) << (step & 31);
-          if ((step & 31) == 31) {          // windows beyond 32,768 samples: empty the mask every 32 steps
-            note_runs(gmask, step - 31);
-            gmask = 0;
-          }
+          if (gmask) note_runs(gmask, g0 / kThreads);
         }
-        note_runs(gmask, step & ~31);
+        // the (< 4) samples after the last whole group: one thread, sample by sample
+        if (tid == (n_full & (kThreads - 1)) && (n & 3)) {
+          uint32_t m = 0;
+          for (int i = 4 * n_full; i < n; ++i) {
+            o[i] = value_of(x[i]);
+            m |= flagged(i) ? 1u : 0u;
+          }
+          if (m) note_runs(1u, n_full / kThreads);
+        }
+      };
+      auto f64_value = [&](int xv) { return static_cast<float>(quot(2 * xv - med2)); };
+      auto f64_x4 = [&](int x4) { return static_cast<float>(quot((x4 >> 1) - med2)); };
+      auto dispatch = [&](auto nf_const, auto value_of, auto value_of_x4) {
+        if (sh == 0) group_loop(std::integral_constant<int, 0>{}, nf_const, value_of, value_of_x4, f64_x4);
+        else if (sh == 1) group_loop(std::integral_constant<int, 1>{}, nf_const, value_of, value_of_x4, f64_x4);
+        else if (sh == 2) group_loop(std::integral_constant<int, 2>{}, nf_const, value_of, value_of_x4, f64_x4);
+        else group_loop(std::integral_constant<int, 3>{}, nf_const, value_of, value_of_x4, f64_x4);
       };
       if (use_lut) {
         const float* lutb = lut - vmin;              // indexed by the sample value itself
-        if (dbg & 16) {
-          // experiment: samples 0 and 2 of a group from the table, 1 and 3 from the float64 pipe
-          group_loop([&](int xv, int e) { return (e & 1) ? static_cast<float>(quot(2 * xv - med2)) : lutb[xv]; });
-        } else {
-          group_loop([&](int xv, int) { return lutb[xv]; });
-        }
+        const uint32_t lut_addr = smem_u32(lut) - 4u * static_cast<uint32_t>(vmin);      // shared-space byte address
+        auto lut_value = [&](int xv) { return lutb[xv]; };
+        auto lut_x4 = [&](int x4) {
+          float f;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(lut_addr + static_cast<uint32_t>(x4)));
+          return f;
+        };
+        if (n_f64 == 2) dispatch(std::integral_constant<int, 2>{}, lut_value, lut_x4);
+        else if (n_f64 == 1) dispatch(std::integral_constant<int, 1>{}, lut_value, lut_x4);
+        else if (n_f64 == 3) dispatch(std::integral_constant<int, 3>{}, lut_value, lut_x4);
+        else dispatch(std::integral_constant<int, 0>{}, lut_value, lut_x4);
       } else {
-        group_loop([&](int xv, int) { return static_cast<float>(quot(2 * xv - med2)); });
+        dispatch(std::integral_constant<int, 4>{}, f64_value, f64_x4);
       }
       __syncthreads();   // every sample has its plain quotient; the runs overwrite theirs
-      const uint32_t n_runs = (dbg & 64) ? 0u : s.n_runs;
+      const uint32_t n_runs = s.n_runs;
       if (n_runs <= static_cast<uint32_t>(kMaxRuns)) {
         for (uint32_t r = tid; r < n_runs; r += kThreads) walk(s.runs[r]);
       } else {             // list overflowed: find the run starts again
@@ -647,6 +680,121 @@ __device__ __forceinline__ void warp_hist_stats(const int (&v)[kPerLane], const 
   __syncwarp();                             // h is cleared again for the warp's next window
 }
 
+// Product path of the poly(A) scan (no per-window statistics requested): riser/preprocess.py:45-72 only needs a
+// window's SUM and whether its MAD exceeds 20, so the exact MAD search and the prefix array are skipped.  The window
+// stays in its packed 16-bit words (8 per lane, word j * 32 + lane of the window's 250); sum, minimum and maximum
+// come from packed SIMD instructions; the histogram is read by ROWS of 32 bins (one bin per lane): the row holding
+// the two middle order statistics is found by adding row totals, the bins inside it by one warp scan.  With
+// d = |2 x - 2 median| and c = #{d <= 40} (three rows at most), 4 MAD = d_(249) + d_(250) > 80 iff c <= 249,
+// <= 80 iff c >= 251; c == 250 (the two statistics straddle 40) is decided from the largest d <= 40 and the smallest
+// d > 40 found in the histogram.  Returns false when the window's range does not fit the histogram (the caller's
+// exact bit-descent path then handles it).
+__device__ __forceinline__ bool warp_window_fast(const uint32_t (&raw)[kPerLane / 2], uint32_t* h, int& sum_out,
+                                                 bool& mad_gt20) {
+  const int lane = threadIdx.x & 31;
+  const bool last_ok = (7 * 32 + lane) < kRes / 2;            // word 7 exists for lanes 0..25 only
+  const uint32_t r7 = last_ok ? raw[7] : raw[0];              // (a copy of a valid word leaves min / max unchanged)
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) sum = __dp2a_lo(static_cast<int>(raw[j]), 0x0101, sum);
+  if (last_ok) sum = __dp2a_lo(static_cast<int>(raw[7]), 0x0101, sum);
+  uint32_t mn2 = __vimin3_s16x2(raw[0], raw[1], raw[2]), mx2 = __vimax3_s16x2(raw[0], raw[1], raw[2]);
+  mn2 = __vimin3_s16x2(mn2, raw[3], raw[4]);
+  mx2 = __vimax3_s16x2(mx2, raw[3], raw[4]);
+  mn2 = __vimin3_s16x2(mn2, raw[5], raw[6]);
+  mx2 = __vimax3_s16x2(mx2, raw[5], raw[6]);
+  mn2 = __vimin3_s16x2(mn2, r7, r7);
+  mx2 = __vimax3_s16x2(mx2, r7, r7);
+  int vmin = min(static_cast<int>(static_cast<int16_t>(mn2 & 0xffffu)), static_cast<int>(mn2) >> 16);
+  int vmax = max(static_cast<int>(static_cast<int16_t>(mx2 & 0xffffu)), static_cast<int>(mx2) >> 16);
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  vmin = __reduce_min_sync(0xffffffffu, vmin);
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  const int range = vmax - vmin;
+  if (range >= kWinBins) return false;
+  sum_out = sum;
+  for (int i = lane; i < ((range + 4) >> 2); i += 32) reinterpret_cast<uint4*>(h)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  const uint32_t h_addr = smem_u32(h) - 4u * static_cast<uint32_t>(vmin);
+  auto count = [&](uint32_t word) {       // both halves of a packed word: bin address = h + 4 (x - vmin)
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(h_addr + static_cast<uint32_t>(static_cast<int>(word << 16) >> 14)) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(h_addr + static_cast<uint32_t>(static_cast<int>(word & 0xffff0000u) >> 14)) : "memory");
+  };
+#pragma unroll
+  for (int j = 0; j < 7; ++j) count(raw[j]);
+  if (last_ok) count(raw[7]);
+  __syncwarp();
+  // ---- the two middle order statistics (0-based ranks 249, 250) as bin indices u1 <= u2
+  const int n_rows = (range + 32) >> 5;
+  uint32_t before = 0, c = 0;
+  int row = 0;
+  for (;; row += 2) {                      // warp-uniform; ends at the latest in the last row (total = 500)
+    // two rows per step: their totals (<= 500 each) travel through one warp reduction as 16-bit halves
+    const int b = 32 * row + lane;
+    const uint32_t c0 = (b <= range) ? h[b] : 0u, c1 = (b + 32 <= range) ? h[b + 32] : 0u;
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, c0 | (c1 << 16));
+    c = c0;
+    if (before + (tot & 0xffffu) >= static_cast<uint32_t>(kRes / 2) || row + 1 >= n_rows) break;
+    before += tot & 0xffffu;
+    c = c1;
+    if (before + (tot >> 16) >= static_cast<uint32_t>(kRes / 2) || row + 2 >= n_rows) {
+      ++row;
+      break;
+    }
+    before += tot >> 16;
+  }
+  uint32_t inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += u;
+  }
+  inc += before;
+  const uint32_t m1 = __ballot_sync(0xffffffffu, inc >= static_cast<uint32_t>(kRes / 2));
+  const uint32_t m2 = __ballot_sync(0xffffffffu, inc >= static_cast<uint32_t>(kRes / 2 + 1));
+  const int u1 = 32 * row + __ffs(m1) - 1;
+  int u2;
+  if (m2) {
+    u2 = 32 * row + __ffs(m2) - 1;
+  } else {                                 // rank 250 is the first occupied bin of a later row
+    u2 = range;
+    for (int r = row + 1; r < n_rows; ++r) {
+      const int b = 32 * r + lane;
+      const uint32_t occ = __ballot_sync(0xffffffffu, b <= range && h[b] != 0u);
+      if (occ) {
+        u2 = 32 * r + __ffs(occ) - 1;
+        break;
+      }
+    }
+  }
+  const int m = u1 + u2;                   // 2 median = 2 vmin + m
+  // ---- c40 = #{u : |2 u - m| <= 40}; the largest such d and the smallest d above 40 for the straddling case
+  const int lo_u = max(0, (m - 40 + 1) >> 1), hi_u = min(range, (m + 40) >> 1);
+  uint32_t c40 = 0;
+  for (int r = lo_u >> 5; r <= (hi_u >> 5); ++r) {
+    const int b = 32 * r + lane;
+    if (b >= lo_u && b <= hi_u) c40 += h[b];
+  }
+  c40 = __reduce_add_sync(0xffffffffu, c40);
+  if (c40 != static_cast<uint32_t>(kRes / 2)) {
+    mad_gt20 = c40 < static_cast<uint32_t>(kRes / 2);
+  } else {
+    int d1 = 0, d2 = 0x7fffffff;           // d1: ranks 0..249 all lie at d <= 40; d2: rank 250 is the smallest d > 40
+    for (int r = 0; r < n_rows; ++r) {
+      const int b = 32 * r + lane;
+      if (b <= range && h[b] != 0u) {
+        const int d = abs(2 * b - m);
+        if (d <= 40) d1 = max(d1, d); else d2 = min(d2, d);
+      }
+    }
+    d1 = __reduce_max_sync(0xffffffffu, d1);
+    d2 = __reduce_min_sync(0xffffffffu, d2);
+    mad_gt20 = d1 + d2 > 80;
+  }
+  __syncwarp();                            // h is cleared again for the warp's next window
+  return true;
+}
+
 __global__ void __launch_bounds__(kPolyaThreads)
 polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
              const int32_t* __restrict__ nsamp, int B, int32_t* __restrict__ polya_end,
@@ -679,13 +827,27 @@ polya_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ off,
       int sum = 0, vmin = 32767, vmax = -32768;
       bool ok[kPerLane];
       if (al4) {
+        uint32_t cur[kPerLane / 2];
+#pragma unroll
+        for (int j = 0; j < kPerLane / 2; ++j) cur[j] = raw[j];
+        if (w + kPolyaWarps < nw) fetch(w + kPolyaWarps);
+        if (!stats) {
+          int fsum;
+          bool gt;
+          if (warp_window_fast(cur, w_hist[warp], fsum, gt)) {
+            if (lane == 0) {
+              w_sum[w] = fsum;
+              w_mad4[w] = gt ? 84 : 80;      // (the scan below only asks whether mad4 / 4 exceeds 20)
+            }
+            continue;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < kPerLane / 2; ++j) {
           ok[2 * j] = ok[2 * j + 1] = (j * 32 + lane) < kRes / 2;
-          v[2 * j] = static_cast<int16_t>(raw[j] & 0xffffu);
-          v[2 * j + 1] = static_cast<int16_t>(raw[j] >> 16);
+          v[2 * j] = static_cast<int16_t>(cur[j] & 0xffffu);
+          v[2 * j + 1] = static_cast<int16_t>(cur[j] >> 16);
         }
-        if (w + kPolyaWarps < nw) fetch(w + kPolyaWarps);
       } else {
 #pragma unroll
         for (int j = 0; j < kPerLane; ++j) {
@@ -868,15 +1030,15 @@ extern "C" int riser_normalise(const int16_t* sig, const int64_t* off, const int
   int per_sm = 0;
   RISER_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normalise_kernel, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  // timing experiments (profiles/README.md): RISER_NORM_CTAS caps the resident CTAs per SM; RISER_NORM_DBG is a
-  // bit mask -- 1 no global stores, 2 no histogram atomics, 4 no normalise loop (all three give WRONG results),
-  // 8 per-sample float64 quotients instead of the value look-up table (same results)
+  // RISER_NORM_CTAS caps the resident CTAs per SM (timing experiments); RISER_NORM_F64 = 0..4 sets how many samples
+  // of every group of four take their quotient from the float64 pipe instead of the per-value look-up table in
+  // shared memory (same results; the table's bank conflicts load the LSU pipe that bounds the kernel, 4 = no table)
   static int ctas_env = -1, dbg = 0;
   if (ctas_env < 0) {
     const char* e = getenv("RISER_NORM_CTAS");
     ctas_env = e ? atoi(e) : 0;
-    e = getenv("RISER_NORM_DBG");
-    dbg = e ? atoi(e) : 0;
+    e = getenv("RISER_NORM_F64");
+    dbg = e ? std::max(0, std::min(4, atoi(e))) : kDefaultF64;
   }
   if (ctas_env > 0) per_sm = std::min(per_sm, ctas_env);
   const int grid = std::min(B, sm_count() * per_sm);

@@ -217,9 +217,9 @@ def test_many_short_reads_with_gaps(proc):
     check_batch(proc, sigs, start=start, length=length)
 
 
-@pytest.mark.parametrize("env", [{"RISER_NORM_NBUF": "2"}, {"RISER_NORM_DBG": "8"}])
+@pytest.mark.parametrize("env", [{"RISER_NORM_NBUF": "2"}, {"RISER_NORM_F64": "4"}, {"RISER_NORM_F64": "2"}])
 def test_normalise_kernel_variants(env):
-    """The two opt-in variants (second staging buffer; per-sample float64 quotients instead of the value table)
+    """The opt-in variants (second staging buffer; all / half of the quotients on the float64 pipe instead of the value table)
     give the same bits.  The switches are read once per process, hence the subprocess."""
     import subprocess
     import sys

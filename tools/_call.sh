@@ -1,11 +1,10 @@
 set -x
-T=r2w
-timeout -s KILL 300 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "every_layer" 2>&1 | tail -5 > gpurun_out/${T}_tests.log
+T=r3a
+timeout -s KILL 600 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${T}_tests.log
 cat gpurun_out/${T}_tests.log
-LE="timeout -s KILL 200 python tools/layer_events.py 4096 16000 3 12"
-$LE warm > /dev/null 2>&1
-for rep in 1 2; do
-$LE res5 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
-RISER_PAIR_RESIDENT=0 $LE nores >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+for seed in 2 3; do
+timeout -s KILL 300 python tools/stress_preprocess.py 1500 $seed 2>&1 | grep -v "^frame" | tail -6 >> gpurun_out/${T}_stress.log
 done
-timeout -s KILL 300 python bench.py --no-cpu-baseline --steps 20 >> gpurun_out/${T}_bench.jsonl 2>/dev/null
+cat gpurun_out/${T}_stress.log
+timeout -s KILL 120 python tools/time_preprocess.py 2>/dev/null | tail -3 > gpurun_out/${T}_pre.log
+cat gpurun_out/${T}_pre.log
