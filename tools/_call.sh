@@ -1,10 +1,11 @@
 set -x
-T=r3a
-timeout -s KILL 600 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${T}_tests.log
+T=r3b
+timeout -s KILL 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${T}_tests.log
 cat gpurun_out/${T}_tests.log
-for seed in 2 3; do
-timeout -s KILL 300 python tools/stress_preprocess.py 1500 $seed 2>&1 | grep -v "^frame" | tail -6 >> gpurun_out/${T}_stress.log
-done
-cat gpurun_out/${T}_stress.log
-timeout -s KILL 120 python tools/time_preprocess.py 2>/dev/null | tail -3 > gpurun_out/${T}_pre.log
-cat gpurun_out/${T}_pre.log
+timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+tail -c 600 gpurun_out/${T}_bench.json
+timeout -s KILL 600 python bench.py --impl reference > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
+cat gpurun_out/${T}_bench_ref.json | cut -c1-400
+timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"fused01|conv_tc|conv_eo|conv_pair" -s 10 -c 10 -o gpurun_out/${T}_conv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out/ | tail -8
