@@ -369,19 +369,32 @@ def run_reads(args, rank, local_rank, world):
     pool = synth.body_batch(1234, P, L)
     mine = shard.shard_indices(np.arange(R), rank, world)
     n_batches = (len(mine) + B - 1) // B
-    hosts = []
-    for k in range(2):      # two pinned staging batches, refilled from the pool per step (the gather is host work
-        hosts.append(torch.empty(B, L, dtype=torch.int16).pin_memory())     # inside the timed region)
+    # Three pinned staging batches, refilled from the pool per step INSIDE the timed region: the gather is the native
+    # threaded one the live path uses (riser_b200/_hostpack, csrc/hostpack.c: buffer protocol + pthreads, GIL released)
+    # and runs one batch ahead in a helper thread, so that the host fill, the H2D copy and the kernels of three
+    # consecutive batches overlap.  (A numpy fancy-index fill on the submitting thread held this mode at 0.2 M
+    # reads/s per GPU: 20 ms of host work per 4 ms of GPU work.)
+    import concurrent.futures
+    from riser_b200.preprocess import _hostpack
+    n_slots = 3
+    hosts = [torch.empty(B, L, dtype=torch.int16).pin_memory() for _ in range(n_slots)]
     pipe = FixedBatchPipeline(clf, B, L, 0.9, "deplete")
+    rows = [pool[i] for i in range(P)]                                 # views, one per pool read
+    byte_off = np.arange(B, dtype=np.int64) * (2 * L)
+    zero_skip = np.zeros(B, dtype=np.int64)
+    take = np.full(B, 2 * L, dtype=np.int64)
+    pack_threads = max(1, min(8, (os.cpu_count() or 2) // max(1, world) - 1))
+    hp = _hostpack()
 
     def fill(k, host):
         idx = mine[k * B:(k + 1) * B]
+        src = ((idx * 40503) % P).tolist()
         hv = host.numpy()
-        src = (idx * 40503) % P
-        hv[:len(idx)] = pool[src]
-        if len(idx) < B:
-            hv[len(idx):] = 0          # constant reads: classified, ignored at the gather
-        return len(idx)
+        n = len(src)
+        hp.pack([rows[j] for j in src], hv.reshape(-1), byte_off[:n], zero_skip[:n], take[:n], pack_threads)
+        if n < B:
+            hv[n:] = 0                 # constant reads: classified, ignored at the gather
+        return n
 
     for k in range(2):
         fill(0, hosts[k])
@@ -402,9 +415,13 @@ def run_reads(args, rank, local_rank, world):
     e0.record()
     pipe.copy_stream.wait_event(e0)
     tickets, counts = [], []
+    filler = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+    pending = filler.submit(fill, 0, hosts[0]) if n_batches else None
     for k in range(n_batches):
-        counts.append(fill(k, hosts[k % 2]))
-        tickets.append(pipe.submit(hosts[k % 2]))
+        counts.append(pending.result())
+        if k + 1 < n_batches:          # slot (k + 1) % 3 was last submitted as batch k - 2, whose result has been read
+            pending = filler.submit(fill, k + 1, hosts[(k + 1) % n_slots])
+        tickets.append(pipe.submit(hosts[k % n_slots]))
         if k >= 1:
             d, pr = pipe.result(tickets[k - 1])
             n = counts[k - 1]
@@ -449,7 +466,7 @@ def run_reads(args, rank, local_rank, world):
                              "data path; decisions gathered once (shard.gather_decisions, 9 B per read)",
                              "decisions_equal_single_gpu": agree, "of": R,
                              "host_gb_per_s_per_rank": len(mine) * L * 2 / host_s / 1e9,
-                             "host_note": "pinned-buffer fill (numpy gather from the read pool) + H2D per rank"},
+                             "host_note": f"pinned-buffer fill (native gather from the read pool, {pack_threads} threads, one batch ahead) + H2D per rank"},
                 "gpu_launches": n_batches * (1 + mdl.launches(B, L) + 1),
                 "clocks": sampler.summary()}
         assert agree == R, f"sharded decisions differ from the single-GPU decisions: {agree} of {R} agree"

@@ -276,14 +276,20 @@ int riser_conv1d_cl(const float* in, const int32_t* len_in, const float* w, cons
 
 /* Valid lengths after every op of the main chain (stem conv, stem max-pool, the convolutions of every block),
  * from the input lengths, in one launch: ksp int32 [n_ops][3] = (kernel, stride, padding) per op, kernel < 0 for
- * MaxPool1d(2, 2, padding 1); out int32 [n_ops][B].  torch's own formulas: Conv1d floor((n + 2p - k) / s) + 1
- * (0 when the window does not fit), pool n / 2 + 1 (resnet.py:79-83).                        */
+ * MaxPool1d(2, 2, padding p); out int32 [n_ops][B].  torch's own formulas: Conv1d floor((n + 2p - k) / s) + 1
+ * (0 when the window does not fit), pool (n + 2p) / 2 (resnet.py:79-83: p = 1; nets/cnn.py:64: p = 0).  */
 int riser_len_chain(const int32_t* len0, int B, const int32_t* ksp, int n_ops, int32_t* out,
                     riser_stream_t stream);
 
 /* MaxPool1d(kernel 2, stride 2, padding 1) -- resnet.py:83.                                 */
 int riser_maxpool1d_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out,
                        int B, int Lin_pad, int Lout_pad, int C, riser_stream_t stream);
+
+/* MaxPool1d(kernel 2, stride 2, padding `pad` in {0, 1}) on the same layout: pad 0 is the pool that ends every
+ * ConvNet layer (nets/cnn.py:64; the generic, non-shipped ConvNet shapes run through these fp32 channel-last ops,
+ * riser_b200/convnet_generic.py), pad 1 the ResNet stem's (resnet.py:83).                     */
+int riser_maxpool1d_pad_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out,
+                           int B, int Lin_pad, int Lout_pad, int C, int pad, riser_stream_t stream);
 
 /* AdaptiveAvgPool1d(1) + Flatten + Linear(C, n_classes) + softmax -- resnet.py:94-98,
  * model.py:27.  probs [B][n_classes]; NaN for len 0.                                        */

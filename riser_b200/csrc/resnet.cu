@@ -138,7 +138,7 @@ conv1d_cl_tiled_kernel(const float* __restrict__ in, const int32_t* __restrict__
 // MaxPool1d(kernel 2, stride 2, padding 1) (resnet.py:83): out[t] = max(in[2t-1], in[2t]), -inf padding
 __global__ void __launch_bounds__(256)
 maxpool_cl_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_in, float* __restrict__ out,
-                  const int32_t* __restrict__ len_out, int B, int Lin_pad, int Lout_pad, int C) {
+                  const int32_t* __restrict__ len_out, int B, int Lin_pad, int Lout_pad, int C, int pad) {
   const int64_t total = static_cast<int64_t>(B) * Lout_pad * C;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -150,7 +150,7 @@ maxpool_cl_kernel(const float* __restrict__ in, const int32_t* __restrict__ len_
     const int Lb = len_in[b];
     const float* inb = in + static_cast<int64_t>(b) * Lin_pad * C + c;
     float m = -INFINITY;
-    const int t0 = 2 * t - 1;
+    const int t0 = 2 * t - pad;
     if (t0 >= 0 && t0 < Lb) m = inb[static_cast<int64_t>(t0) * C];
     if (t0 + 1 < Lb) m = fmaxf(m, inb[static_cast<int64_t>(t0 + 1) * C]);
     out[idx] = m;
@@ -255,7 +255,8 @@ gap_linear_softmax_kernel(const float* __restrict__ in, const int32_t* __restric
 }
 
 // Valid lengths after every op of the network's main chain, from the input lengths: op j is Conv1d(k, stride, pad)
-// (floor((n + 2 pad - k) / stride) + 1, clamped at 0) or, k < 0, MaxPool1d(2, 2, padding 1) (n / 2 + 1; 0 stays 0).
+// (floor((n + 2 pad - k) / stride) + 1, clamped at 0) or, k < 0, MaxPool1d(2, 2, padding pad) ((n + 2 pad) / 2: n / 2 + 1
+// with the ResNet stem's padding 1, n / 2 for the ConvNet's unpadded pool; 0 stays 0).
 __global__ void len_chain_kernel(const int32_t* __restrict__ len0, int B, const int32_t* __restrict__ ksp, int n_ops,
                                  int32_t* __restrict__ out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,7 +265,7 @@ __global__ void len_chain_kernel(const int32_t* __restrict__ len0, int B, const 
   for (int j = 0; j < n_ops; ++j) {
     const int k = ksp[3 * j], st = ksp[3 * j + 1], pd = ksp[3 * j + 2];
     if (k < 0) {
-      n = n > 0 ? n / 2 + 1 : 0;
+      n = n > 0 ? (n + 2 * pd) / 2 : 0;
     } else {
       const int num = n + 2 * pd - k;
       n = num >= 0 ? num / st + 1 : 0;
@@ -332,13 +333,21 @@ extern "C" int riser_conv1d_cl(const float* in, const int32_t* len_in, const flo
   return RISER_OK;
 }
 
-extern "C" int riser_maxpool1d_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out, int B,
-                                  int Lin_pad, int Lout_pad, int C, riser_stream_t stream) {
-  RISER_REQUIRE(in && len_in && out && len_out, "riser_maxpool1d_cl: null pointer");
+extern "C" int riser_maxpool1d_pad_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out, int B,
+                                      int Lin_pad, int Lout_pad, int C, int pad, riser_stream_t stream) {
+  RISER_REQUIRE(in && len_in && out && len_out, "riser_maxpool1d_pad_cl: null pointer");
+  RISER_REQUIRE(pad == 0 || pad == 1, "riser_maxpool1d_pad_cl: padding %d (0 or 1)", pad);
   const int64_t total = static_cast<int64_t>(B) * Lout_pad * C;
-  maxpool_cl_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(in, len_in, out, len_out, B, Lin_pad, Lout_pad, C);
+  if (total == 0) return RISER_OK;
+  maxpool_cl_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(in, len_in, out, len_out, B, Lin_pad, Lout_pad, C,
+                                                                    pad);
   RISER_CUDA_TRY(cudaGetLastError());
   return RISER_OK;
+}
+
+extern "C" int riser_maxpool1d_cl(const float* in, const int32_t* len_in, float* out, const int32_t* len_out, int B,
+                                  int Lin_pad, int Lout_pad, int C, riser_stream_t stream) {
+  return riser_maxpool1d_pad_cl(in, len_in, out, len_out, B, Lin_pad, Lout_pad, C, 1, stream);
 }
 
 extern "C" int riser_stem_pool_cl(const float* x, int64_t ld_x, const int32_t* len_in, const float* w, const float* bias,

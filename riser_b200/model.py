@@ -115,11 +115,17 @@ class Model():
     def _build(self, sd, c):
         """Shape checks mirror what ConvNet(config.cnn).load_state_dict would enforce
         (riser/nets/cnn.py:8-41, riser/model.py:18-19)."""
-        if c.classifier != 'gap_fc' or c.depth != 1 or c.n_classes != 2:
-            raise NotImplementedError("riser_b200 implements the shipped ConvNet shape: depth 1, "
-                                      "'gap_fc' classifier, 2 classes (riser/model/*.yaml:6-12)")
-        if any(k != 3 for k in c.kernels[:c.n_layers]):
-            raise NotImplementedError("riser_b200 implements kernel size 3 (riser/model/*.yaml:10)")
+        self._generic = None
+        if (c.classifier != 'gap_fc' or int(c.depth) != 1 or int(c.n_classes) != 2
+                or any(int(k) != 3 for k in c.kernels[:c.n_layers]) or int(c.n_layers) < 2):
+            # not the shipped shape (riser/model/*.yaml:6-12) the kernels of csrc/convnet.cu are written for: depth > 1,
+            # other odd kernel sizes, 'gap' head, n_classes != 2 run on the generic channel-last ops
+            # (riser/nets/cnn.py:8-65 in full; convnet_generic.py says what is still refused and why)
+            from .convnet_generic import GenericConvNet
+            self._generic = GenericConvNet(sd, c, self.device, self.logger)
+            self.channels = [int(x) for x in c.channels[:int(c.n_layers)]]
+            self.n_layers = int(c.n_layers)
+            return
         n = int(c.n_layers)
         channels = [int(x) for x in c.channels[:n]]
         expected = {}
@@ -177,6 +183,10 @@ class Model():
         """riser/model.py:22-28: 1-D numpy (float64, or int64 zeros) -> Tensor[2] =
         (p_off_target, p_on_target) on the device."""
         signal = np.asarray(signal)
+        if self._generic is not None:
+            if signal.ndim != 1 or signal.shape[0] < self._generic.min_length:
+                raise RuntimeError(f"signal of length {signal.shape} is shorter than {self._generic.min_length} samples")
+            return self._generic.classify(signal)
         if signal.ndim != 1 or signal.shape[0] < MIN_LENGTH:
             # the reference dies in the 12th MaxPool1d for shorter input
             raise RuntimeError(f"signal of length {signal.shape} is shorter than {MIN_LENGTH} samples")
@@ -198,6 +208,8 @@ class Model():
         events: optional list; (start, end) torch.cuda.Event pairs bracketing layer 0 +
         the tcgen05 conv layers of every sub-batch are appended (bench.py's roofline;
         ``time_layer0`` gives the layer-0 share to subtract)."""
+        if self._generic is not None:
+            return self._generic.classify_batch(x, lens, max_len=max_len, probs=probs)
         B = x.shape[0]
         max_len = int(max_len if max_len is not None else x.shape[1])
         if probs is None:
@@ -245,6 +257,8 @@ class Model():
         """Kernels one classify_batch call launches."""
         if B <= 0:
             return 0
+        if self._generic is not None:
+            return self._generic.launches(B)
         chunk = int(chunk or DEFAULT_CHUNK or B)
         return sum(self.plan(min(chunk, B - lo), max_len).launches for lo in range(0, B, chunk))
 

@@ -145,6 +145,42 @@ def save_state_dict(seed, path):
     return path
 
 
+# ---------------------------------------------------------------- ConvNet shapes beyond the shipped one
+GENERIC_CNN_CONFIGS = {
+    # riser/nets/cnn.py in full: depth > 1, kernel sizes other than 3, 'gap' head, n_classes != 2 (the reference
+    # ships only the 12 x k3 depth-1 'gap_fc' two-class configuration; these exercise the rest of its constructor)
+    "deep_gap": dict(n_layers=4, depth=2, channels=[8, 12, 18, 27], kernels=[5, 3, 7, 3], n_classes=3, classifier="gap"),
+    "k5_fc": dict(n_layers=5, depth=1, channels=[10, 15, 22, 33, 50], kernels=[3, 5, 3, 5, 3], n_classes=2, classifier="gap_fc"),
+    "wide_d3": dict(n_layers=3, depth=3, channels=[16, 40, 96], kernels=[3, 3, 3], n_classes=4, classifier="gap_fc"),
+}
+
+
+def generic_cnn_state_dict(cfg, seed, as_torch=True):
+    """Seeded state-dict with the key names and shapes ConvNet(cfg) has (riser/nets/cnn.py:13-41,52-65): He-normal
+    conv weights, small biases, a head scaled so that the class probabilities spread instead of saturating."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    sd = {}
+    cin = 1
+    for i in range(cfg["n_layers"]):
+        cout, k = cfg["channels"][i], cfg["kernels"][i]
+        for d in range(cfg["depth"]):
+            ci = cin if d == 0 else cout
+            sd[f"layers.{i}.{2 * d}.weight"] = rng.normal(0.0, np.sqrt(2.0 / (ci * k)), size=(cout, ci, k)).astype(np.float32)
+            sd[f"layers.{i}.{2 * d}.bias"] = rng.normal(0.0, 0.05, size=(cout,)).astype(np.float32)
+        cin = cout
+    nc = cfg["n_classes"]
+    w = rng.normal(0.0, 2.0 / np.sqrt(cin), size=(nc, cin)).astype(np.float32)
+    b = rng.normal(0.0, 0.3, size=(nc,)).astype(np.float32)
+    if cfg["classifier"] == "gap":
+        sd["classifier.0.weight"], sd["classifier.0.bias"] = w[:, :, None].copy(), b
+    else:
+        sd["classifier.2.weight"], sd["classifier.2.bias"] = w, b
+    if as_torch:
+        import torch
+        sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    return sd
+
+
 # ---------------------------------------------------------------- ResNet variant (riser/nets/resnet.py)
 RESNET_CONFIGS = {
     # the reference ships no resnet config; these two exercise both block types.
