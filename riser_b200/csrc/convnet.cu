@@ -117,6 +117,7 @@ struct ConvArgs {
   int a_stages, b_stages, acc_stages, resident;
   int epi_sets;           // epilogue warp sets (each = 4 warps covering the TMEM lane quadrants)
   int dual;               // conv_tc_kernel, MS == 2: one MMA-issuing thread PER SUB-TILE (warp 1 and the last warp)
+  int dbg_skip;           // conv_pair_kernel timing experiments (WRONG results): 1 = no weight loads, 2 = no activation loads
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
@@ -2258,10 +2259,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int kb = 0; kb < a.k_blocks; ++kb) {
           const bool is8 = kb >= a.kb16;
           mbar_wait(&s.a_empty[sa], pa ^ 1);
-          if (leader) mbar_arrive_expect_tx(&s.a_full[sa], 2 * MS * kATile);
+          if (a.dbg_skip & 2) {
+            if (leader) mbar_arrive(&s.a_full[sa]);
+          } else if (leader) {
+            mbar_arrive_expect_tx(&s.a_full[sa], 2 * MS * kATile);
+          }
           unsigned char* dst = a_ring + static_cast<size_t>(sa) * kAGroup;
 #pragma unroll
           for (int ms = 0; ms < MS; ++ms) {
+            if (a.dbg_skip & 2) break;
             if (is8)
               tma_load_2d_pair(dst + ms * kATile, &tm_a8, &s.a_full[sa], 2 * a.cin_p + (kb - a.kb16) * 128, m0 + ms * 256);
             else
@@ -2275,13 +2281,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int tap = 0; tap < 3; ++tap) {
             if (a.resident) break;
             mbar_wait(&s.b_empty[sb], pb ^ 1);
-            if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_tx);
-            if (is8)
-              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb8, &s.b_full[sb], (kb - a.kb16) * 128,
-                               tap * a.cout_p + n0);
-            else
-              tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb, &s.b_full[sb], kb * 64,
-                               tap * a.cout_p + n0);
+            if (a.dbg_skip & 1) {
+              if (leader) mbar_arrive(&s.b_full[sb]);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&s.b_full[sb], 2 * b_tx);
+              if (is8)
+                tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb8, &s.b_full[sb], (kb - a.kb16) * 128,
+                                 tap * a.cout_p + n0);
+              else
+                tma_load_2d_pair(b_region + static_cast<size_t>(sb) * b_bytes, tb, &s.b_full[sb], kb * 64,
+                                 tap * a.cout_p + n0);
+            }
             if (++sb == a.b_stages) {
               sb = 0;
               pb ^= 1;
@@ -3025,6 +3035,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.b_stages = std::max(2, std::min<int>(kMaxBStages, static_cast<int>((avail - a.a_stages * a_group) / half_b)));
       a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
       a.dual = (a.ms == 2 && env_int("RISER_DUAL_ISSUE", 1)) ? 1 : 0;
+      a.dbg_skip = env_int("RISER_PAIR_DBG_SKIP", 0);       // timing experiments only
       a.resident = 0;
       size_t b_total = a.b_stages * half_b;
       const size_t w_half = static_cast<size_t>(3) * a.k_blocks * half_b;      // this CTA's half of every tap and K block
