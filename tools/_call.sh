@@ -1,12 +1,12 @@
 set -x
-T=r3e
-LE="timeout -s KILL 200 python tools/layer_events.py 4096 16000 3 12"
-$LE warm > /dev/null 2>&1
-for d in 0 1 2 3 0; do
-RISER_PAIR_DBG_SKIP=$d $LE skip$d >> gpurun_out/${T}_layers.jsonl 2>/dev/null
-done
-python - <<'P'
-import json
-for l in open('gpurun_out/r3e_layers.jsonl'):
-    d=json.loads(l); print(d['tag'], {k:round(v,3) for k,v in d['layer_ms'].items() if int(k.split(':')[0])>=5}, round(d['conv_ms'],3))
-P
+T=r3j
+timeout -s KILL 120 python tools/batch_invariance.py 96 > gpurun_out/${T}_inv.log 2>&1
+tail -25 gpurun_out/${T}_inv.log
+timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_FUSE23=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nofuse23.log
+cat gpurun_out/${T}_inv_nofuse23.log
+timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_PAIR=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nopair.log
+cat gpurun_out/${T}_inv_nopair.log
+timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_KC=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nokc.log
+cat gpurun_out/${T}_inv_nokc.log
+timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_LIVE_GRAPHS=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nograph.log
+cat gpurun_out/${T}_inv_nograph.log
