@@ -1,12 +1,13 @@
 set -x
-T=r3j
-timeout -s KILL 120 python tools/batch_invariance.py 96 > gpurun_out/${T}_inv.log 2>&1
-tail -25 gpurun_out/${T}_inv.log
-timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_FUSE23=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nofuse23.log
-cat gpurun_out/${T}_inv_nofuse23.log
-timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_PAIR=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nopair.log
-cat gpurun_out/${T}_inv_nopair.log
-timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_KC=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nokc.log
-cat gpurun_out/${T}_inv_nokc.log
-timeout -s KILL 120 python tools/batch_invariance.py 96 RISER_LIVE_GRAPHS=0 2>&1 | tail -4 > gpurun_out/${T}_inv_nograph.log
-cat gpurun_out/${T}_inv_nograph.log
+T=r3m
+timeout -s KILL 200 python -m pytest tests/test_gpu_resnet.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_tests.log
+cat gpurun_out/${T}_tests.log
+grep -q failed gpurun_out/${T}_tests.log && exit 1
+for rep in 1 2; do
+timeout -s KILL 100 python tools/time_resnet.py 512 12048 basic 2>/dev/null | tail -1 >> gpurun_out/${T}_resnet.log
+done
+timeout -s KILL 100 python tools/time_resnet.py 4096 12048 basic 2>/dev/null | tail -1 >> gpurun_out/${T}_resnet.log
+timeout -s KILL 100 python tools/time_resnet.py 512 12048 bottleneck 2>/dev/null | tail -1 >> gpurun_out/${T}_resnet.log
+cat gpurun_out/${T}_resnet.log
+timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_resnet_launches.csv python tools/time_resnet.py 512 12048 basic > /dev/null 2>&1
+python tools/summarise_ncu.py launches gpurun_out/${T}_resnet_launches.csv | head -8
