@@ -148,6 +148,54 @@ def test_polya_random_vs_oracle(proc):
     assert list(ends) == want
 
 
+def test_polya_decision_only_path_corner_windows(proc):
+    """The product path of riser_polya_end (no statistics requested) decides MAD > 20 from one count around the median
+    instead of computing the MAD (csrc/preprocess.cu warp_window_fast).  Windows built to sit on its edges -- exactly
+    250 samples within 20 of the median with the two middle distances summing to more than 80, MADs of exactly 20 and
+    20.5, value ranges of 1,022 .. 1,025 (the histogram's limit), flat and two-valued windows, negative values -- must
+    give the same ends as the statistics path and the oracle (riser/preprocess.py:42-79)."""
+    rng = np.random.default_rng(11)
+
+    def window(values, counts):
+        w = np.repeat(np.array(values, dtype=np.int64), counts)
+        assert len(w) == 500
+        return rng.permutation(w)
+
+    kinds = [
+        window([400, 490, 510, 600], [125, 125, 125, 125]),        # c = 250, d1 + d2 = 40 + 400 -> MAD > 20
+        window([475, 490, 510, 525], [125, 125, 125, 125]),        # c = 250, d1 + d2 = 40 + 100 > 80
+        window([480, 490, 510, 520], [125, 125, 125, 125]),        # all within 20 of the median: MAD 15
+        window([480, 500, 520], [125, 250, 125]),                  # MAD = 10 (c = 500)
+        window([460, 479, 521, 540], [125, 125, 125, 125]),        # d1 = 42: c = 0
+        window([459, 480, 520, 541], [120, 130, 130, 120]),        # MAD exactly 20 -> not > 20
+        window([459, 480, 521, 541], [120, 130, 130, 120]),        # MAD 20.5 -> > 20
+        window([0, 500, 1022], [100, 300, 100]),                   # range 1,022: histogram path
+        window([0, 500, 1023], [100, 300, 100]),                   # range 1,023: its last bin
+        window([0, 500, 1024], [100, 300, 100]),                   # range 1,024: bit-descent path
+        window([-300, -280, -260, 725], [200, 100, 100, 100]),     # negative values, wide range
+        window([431], [500]),                                      # flat
+        window([431, 432], [250, 250]),                            # two values, median between them
+        window([431, 432], [249, 251]),
+    ]
+    sigs = []
+    for k in range(40):
+        n_win = int(rng.integers(3, 30))
+        parts = []
+        for _ in range(n_win):
+            if rng.random() < 0.5:
+                parts.append(kinds[int(rng.integers(len(kinds)))] + int(rng.integers(-3, 4)) * int(rng.random() < 0.3))
+            else:
+                parts.append(np.rint(rng.normal(rng.choice([450, 620, 700]), rng.choice([4, 14, 27, 60]), size=500)).astype(np.int64))
+        tail = np.rint(rng.normal(500, 30, size=int(rng.integers(0, 499)))).astype(np.int64)
+        sigs.append(np.clip(np.concatenate(parts + [tail]), -32768, 32767).astype(np.int16))
+    ends_fast = proc.get_polyA_end_batch(sigs)
+    ends_stats, _ = proc.get_polyA_end_batch(sigs, return_stats=True)
+    want = [(-1 if pp.polya_end(s) is None else pp.polya_end(s)) for s in sigs]
+    assert list(ends_stats) == want
+    assert list(ends_fast) == want
+    assert sum(e > 0 for e in want) >= 5 and sum(e < 0 for e in want) >= 5
+
+
 def test_retrain_float32_normalise_bit_exact(golden_dir):
     """csrc/normalise_f32.cu against the reference's riser/retrain/preprocess.py outputs."""
     from oracle import retrain_oracle as rt
