@@ -109,25 +109,39 @@ struct StagedWindow {
 // low bits inside the located bin.  Block-uniform control flow; all threads get r1, r2.
 template <class KeyFn>
 __device__ int select_two(KeyFn key, const StagedWindow& win, uint32_t maxkey, uint32_t k1, uint32_t k2,
-                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false) {
+                          SelectScratch& s, uint32_t& r1, uint32_t& r2, bool keep_prefix = false, int rot = -1) {
+  // rot >= 0: the histogram of the keys is already in s.hist, CIRCULAR -- key u sits in bin (u + rot) & (kBins - 1)
+  // (the fused min / max + histogram pass of the normalise kernel bins by `sample & (kBins - 1)` before it knows the
+  // minimum; maxkey < kBins then) -- and published by a block barrier; the prefix is written back in the same order.
   const int tid = threadIdx.x;
   int shift = 0;
   while ((maxkey >> shift) >= static_cast<uint32_t>(kBins)) ++shift;
-  for (int i = tid; i < kBins / 4; i += kThreads) reinterpret_cast<uint4*>(s.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  if (shift == 0) {       // (every real squiggle window: no shift instruction per sample)
-    win.for_each([&](int e) { atomicAdd(&s.hist[key(e)], 1u); });
-  } else {
-    win.for_each([&](int e) { atomicAdd(&s.hist[key(e) >> shift], 1u); });
+  const bool prebuilt = rot >= 0;
+  if (!prebuilt) {
+    rot = 0;
+    for (int i = tid; i < kBins / 4; i += kThreads) reinterpret_cast<uint4*>(s.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (shift == 0) {       // (every real squiggle window: no shift instruction per sample)
+      win.for_each([&](int e) { atomicAdd(&s.hist[key(e)], 1u); });
+    } else {
+      win.for_each([&](int e) { atomicAdd(&s.hist[key(e) >> shift], 1u); });
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  // Thread t owns the aligned block of 8 bins (t + rot / 8) mod 256, i.e. the keys 8 t - rot % 8 .. + 7: contiguous in key
+  // order, read and written back with 16-byte accesses.  (The rot % 8 bins thread 0 holds "before key 0" are the top
+  // keys wrapped around: the caller only passes rot when maxkey < kBins - 8, so they are empty.)
+  static_assert(kBinsPerThread == 8, "two uint4 per thread");
+  const int phys = ((tid + (rot >> 3)) & (kThreads - 1)) * kBinsPerThread;
+  const int key0 = tid * kBinsPerThread - (rot & 7);
   uint32_t c[kBinsPerThread];
   uint32_t local = 0;
-#pragma unroll
-  for (int j = 0; j < kBinsPerThread; ++j) {
-    c[j] = s.hist[tid * kBinsPerThread + j];
-    local += c[j];
+  {
+    const uint4 lo = *reinterpret_cast<const uint4*>(&s.hist[phys]), hi = *reinterpret_cast<const uint4*>(&s.hist[phys + 4]);
+    c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
   }
+#pragma unroll
+  for (int j = 0; j < kBinsPerThread; ++j) local += c[j];
   const uint32_t ex = block_exclusive_scan(local, s.warp_sums);
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
@@ -137,7 +151,7 @@ __device__ int select_two(KeyFn key, const StagedWindow& win, uint32_t maxkey, u
 #pragma unroll
       for (int j = 0; j < kBinsPerThread; ++j) {
         if (k >= run && k < run + c[j]) {
-          s.res[2 * which] = tid * kBinsPerThread + j;
+          s.res[2 * which] = static_cast<uint32_t>(key0 + j);
           s.res[2 * which + 1] = run;
         }
         run += c[j];
@@ -154,8 +168,10 @@ __device__ int select_two(KeyFn key, const StagedWindow& win, uint32_t maxkey, u
 #pragma unroll
       for (int j = 0; j < kBinsPerThread; ++j) {
         run += c[j];
-        s.hist[tid * kBinsPerThread + j] = run;
+        c[j] = run;
       }
+      *reinterpret_cast<uint4*>(&s.hist[phys]) = make_uint4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<uint4*>(&s.hist[phys + 4]) = make_uint4(c[4], c[5], c[6], c[7]);
     }
     __syncthreads();
     return 0;
@@ -268,37 +284,57 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 1) & 7);
     const int16_t* stage = stage_base + static_cast<size_t>(buf) * buf_samples;
     const StagedWindow x{stage, a, n};     // x[i] == g[i]
+    // (the value histogram of the fused pass below is cleared while the read's copy is in flight)
+    for (int i = tid; i < kBins / 4; i += kThreads) reinterpret_cast<uint4*>(s.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
     mbar_wait(&s.bar[buf], (phase_bits >> buf) & 1u);
     phase_bits ^= 1u << buf;
+    __syncthreads();
 
-    // ---- min / max of the window (packed 16-bit lanes for whole chunks)
+    // ---- min / max of the window AND its value histogram in one pass over the staged chunks: a sample is counted in
+    //      bin `x & (kBins - 1)` -- circular, so the minimum need not be known yet; if the range turns out to fit the
+    //      bins (every real squiggle) the bins of the values vmin .. vmax are distinct and bin u of the usual
+    //      histogram is (u + vmin) & (kBins - 1); otherwise the select below rebuilds a shifted histogram.
+    //      (The bins were cleared before the copy wait; the barrier above orders that against these atomics.)
     int vmin = 32767, vmax = -32768;
     {
       uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
-      const uint4* s4 = reinterpret_cast<const uint4*>(stage);
-      const int end = a + n;
-      const int n_chunks = (end + 7) >> 3;
-      for (int c = tid; c < n_chunks; c += kThreads) {
-        const uint4 v = s4[c];
-        const int base = 8 * c;
-        if (base >= a && base + 8 <= end) {
-          mn2 = __vimin3_s16x2(mn2, v.x, v.y);
-          mn2 = __vimin3_s16x2(mn2, v.z, v.w);
-          mx2 = __vimax3_s16x2(mx2, v.x, v.y);
-          mx2 = __vimax3_s16x2(mx2, v.z, v.w);
-        } else {
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const uint32_t hist_addr = smem_u32(s.hist);
+      auto count4 = [&](uint32_t four_x) {      // four_x = 4 * sample (any upper bits): bin byte offset = four_x & 4 (kBins - 1)
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_addr + (four_x & (4u * (kBins - 1)))) : "memory");
+      };
+      auto one = [&](int e) {
+        vmin = min(vmin, e);
+        vmax = max(vmax, e);
+        count4(static_cast<uint32_t>(e) << 2);
+      };
+      auto full = [&](int c) {
+        const uint4 v = reinterpret_cast<const uint4*>(stage)[c];
+        mn2 = __vimin3_s16x2(mn2, v.x, v.y);
+        mn2 = __vimin3_s16x2(mn2, v.z, v.w);
+        mx2 = __vimax3_s16x2(mx2, v.x, v.y);
+        mx2 = __vimax3_s16x2(mx2, v.z, v.w);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int p = base + j;
-            if (p >= a && p < end) {
-              const int e = static_cast<int16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-              vmin = min(vmin, e);
-              vmax = max(vmax, e);
-            }
-          }
+        for (int j = 0; j < 4; ++j) {
+          count4(w[j] << 2);                    // lower half: bits 2 .. 12 of (w << 2) are 4 * (x & 2047)
+          count4(w[j] >> 14);                   // upper half
         }
+      };
+      // the chunk order of StagedWindow::for_each (lane-decorrelated, edge samples one per thread)
+      const int end = a + n;
+      const int c_first = (a + 7) >> 3, c_last = end >> 3;
+      const int head_end = min(end, 8 * c_first), tail_start = max(8 * c_last, head_end);
+      if (tid < 16) {
+        const int pos = (tid < 8) ? a + tid : tail_start + tid - 8;
+        if (pos < ((tid < 8) ? head_end : end)) one(static_cast<int>(stage[pos]));
       }
+      const int n_full = max(c_last - c_first, 0);
+      const int R = (n_full + kWarps - 1) / kWarps;
+      const int c0 = c_first + warp * R, c1 = min(c0 + R, c_first + n_full);
+      int S = (c1 - c0) >> 5;
+      S = (S > 0) ? ((S - 1) | 1) : 0;
+      for (int i = 0; i < S; ++i) full(c0 + lane * S + i);
+      for (int c = c0 + 32 * S + lane; c < c1; c += 32) full(c);
       vmin = min(vmin, min(static_cast<int>(static_cast<int16_t>(mn2 & 0xffffu)), static_cast<int>(static_cast<int16_t>(mn2 >> 16))));
       vmax = max(vmax, max(static_cast<int>(static_cast<int16_t>(mx2 & 0xffffu)), static_cast<int>(static_cast<int16_t>(mx2 >> 16))));
     }
@@ -308,7 +344,7 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       s.red[warp] = vmin;
       s.red[kWarps + warp] = vmax;
     }
-    __syncthreads();
+    __syncthreads();          // (also publishes the histogram)
     vmin = s.red[0];
     vmax = s.red[kWarps];
 #pragma unroll
@@ -321,8 +357,10 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
     const uint32_t k1 = static_cast<uint32_t>((n - 1) >> 1), k2 = static_cast<uint32_t>(n >> 1);
     uint32_t r1, r2;
     const int range = vmax - vmin;
+    const int rot = (range < kBins - 8) ? (vmin & (kBins - 1)) : -1;      // circular histogram usable as it stands?
+    const int rot_eff = max(rot, 0);      // bin of key u in the histogram the select leaves behind (shift 0): (u + rot_eff) & (kBins - 1)
     const int shift_used = select_two([&](int e) { return static_cast<uint32_t>(e - vmin); }, x,
-                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true);
+                                      static_cast<uint32_t>(range), k1, k2, s, r1, r2, true, rot);
     const int med2 = 2 * vmin + static_cast<int>(r1 + r2);
 
     // ---- MAD on keys d = |2x - med2| = 2|x - median| -> mad4 = 4 * MAD (exact)
@@ -342,7 +380,7 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
           const int d = min(lo_d + (lane + 1) * step - 1, hi_d);
           const int hi_u = min((m + d) >> 1, range);
           const int lo_u = (m - d + 1) >> 1;              // ceil((m - d) / 2), may be <= 0
-          const uint32_t cnt = s.hist[hi_u] - (lo_u > 0 ? s.hist[lo_u - 1] : 0u);
+          const uint32_t cnt = s.hist[(hi_u + rot_eff) & (kBins - 1)] - (lo_u > 0 ? s.hist[(lo_u - 1 + rot_eff) & (kBins - 1)] : 0u);
           const uint32_t okm = __ballot_sync(0xffffffffu, cnt >= want);   // lane 31 probes hi_d: never empty
           const int f = __ffs(okm) - 1;
           hi_d = min(lo_d + (f + 1) * step - 1, hi_d);
@@ -395,7 +433,8 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
       const bool use_lut = (shift_used == 0) && n_f64 < 4;
       float* lut = reinterpret_cast<float*>(s.hist);
       if (use_lut)
-        for (int u = tid; u <= range; u += kThreads) lut[u] = static_cast<float>(quot(2 * (vmin + u) - med2));
+        for (int u = tid; u <= range; u += kThreads)      // (circular by VALUE: the entry of sample value v sits at v & (kBins - 1))
+          lut[(vmin + u) & (kBins - 1)] = static_cast<float>(quot(2 * (vmin + u) - med2));
 
       // ---- outlier threshold in the integer key domain: |z| > 3.5  <=>  d > dthr, where
       //      z = fl((d/2) / denom) is monotone in d.  Found once per read with exact divides: the lanes of
@@ -539,12 +578,11 @@ normalise_kernel(const int16_t* __restrict__ sig, const int64_t* __restrict__ of
         else group_loop(std::integral_constant<int, 3>{}, nf_const, value_of, value_of_x4, f64_x4);
       };
       if (use_lut) {
-        const float* lutb = lut - vmin;              // indexed by the sample value itself
-        const uint32_t lut_addr = smem_u32(lut) - 4u * static_cast<uint32_t>(vmin);      // shared-space byte address
-        auto lut_value = [&](int xv) { return lutb[xv]; };
+        const uint32_t lut_addr = smem_u32(lut);      // shared-space byte address; entry of value v at 4 (v & (kBins - 1))
+        auto lut_value = [&](int xv) { return lut[xv & (kBins - 1)]; };
         auto lut_x4 = [&](int x4) {
           float f;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(lut_addr + static_cast<uint32_t>(x4)));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(lut_addr + (static_cast<uint32_t>(x4) & (4u * (kBins - 1)))));
           return f;
         };
         if (n_f64 == 2) dispatch(std::integral_constant<int, 2>{}, lut_value, lut_x4);

@@ -103,6 +103,28 @@ def test_random_stress_wide_ranges(proc):
     check_batch(proc, sigs)
 
 
+def test_value_ranges_around_the_histogram_limits(proc):
+    """The normalise kernel bins a window by `sample & 2047` before it knows the minimum (fused min / max + histogram
+    pass): exact while the range stays below 2,040; between 2,040 and 2,047 the histogram is rebuilt relative to the
+    minimum, from 2,048 on it is a shifted histogram with a refinement pass.  Windows on both sides of every limit, with
+    minima on both sides of the bins' wrap-around (multiples of 2,048, negative values), outliers included."""
+    rng = np.random.default_rng(33)
+    sigs = []
+    for span in (1, 2, 7, 8, 9, 1000, 2038, 2039, 2040, 2041, 2046, 2047, 2048, 2049, 4095, 4096, 9000):
+        for lo in (-2048 - 5, -2048, -1030, -7, 0, 3, 2040, 2047, 2048, 4090, 20000):
+            if lo + span > 32767:
+                continue
+            n = int(rng.integers(4096, 9000))
+            x = rng.normal(lo + span / 2.0, max(span / 9.0, 0.6), size=n)
+            x = np.clip(np.rint(x), lo, lo + span)
+            x[rng.integers(0, n, size=3)] = lo                  # the extremes are attained
+            x[rng.integers(0, n, size=3)] = lo + span
+            sigs.append(x.astype(np.int16))
+    start = rng.integers(0, 9, size=len(sigs)).astype(np.int32)         # every 16-byte phase
+    length = np.array([len(s) - st for s, st in zip(sigs, start)], dtype=np.int32)
+    check_batch(proc, sigs, start=start, length=length)
+
+
 def test_polya_end_matches_reference(proc, golden_dir):
     g = np.load(os.path.join(golden_dir, "polya.npz"))
     reads = P.polya_reads()
