@@ -1,2 +1,14 @@
 set -x
-timeout -s KILL 300 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -5
+T=r3y
+timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_tests.log
+cat gpurun_out/${T}_tests.log
+grep -q failed gpurun_out/${T}_tests.log && exit 1
+timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/r3y_bench.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['frac_burst'], d['e2e']['value'], d['roofline_normalise']['frac'], d['clocks'])
+P
+timeout -s KILL 600 python bench.py --impl reference > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
+timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:normalise -s 3 -c 1 -o gpurun_out/${T}_norm python tools/time_normalise.py > /dev/null 2>&1
+du -sh gpurun_out
