@@ -287,7 +287,7 @@ def test_many_short_reads_with_gaps(proc):
     check_batch(proc, sigs, start=start, length=length)
 
 
-@pytest.mark.parametrize("env", [{"RISER_NORM_NBUF": "2"}, {"RISER_NORM_F64": "4"}, {"RISER_NORM_F64": "2"}])
+@pytest.mark.parametrize("env", [{"RISER_NORM_NBUF": "2"}, {"RISER_NORM_F64": "4"}, {"RISER_NORM_F64": "2"}, {"RISER_NORM_F64": "0"}])
 def test_normalise_kernel_variants(env):
     """The opt-in variants (second staging buffer; all / half of the quotients on the float64 pipe instead of the value table)
     give the same bits.  The switches are read once per process, hence the subprocess."""

@@ -1,14 +1,8 @@
 set -x
-T=r3y
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_tests.log
+T=r4a
+timeout -s KILL 300 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_tests.log
 cat gpurun_out/${T}_tests.log
 grep -q failed gpurun_out/${T}_tests.log && exit 1
-timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
-python - <<'P'
-import json
-d=json.load(open('gpurun_out/r3y_bench.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['frac_burst'], d['e2e']['value'], d['roofline_normalise']['frac'], d['clocks'])
-P
-timeout -s KILL 600 python bench.py --impl reference > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
-timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:normalise -s 3 -c 1 -o gpurun_out/${T}_norm python tools/time_normalise.py > /dev/null 2>&1
-du -sh gpurun_out
+timeout -s KILL 200 python tools/stress_preprocess.py 1500 9 2>&1 | grep -v "^frame" | tail -3
+timeout -s KILL 100 python tools/time_normalise.py 2>/dev/null | tail -1 | cut -c1-120
+timeout -s KILL 100 python tools/time_preprocess.py 2>/dev/null | tail -2
