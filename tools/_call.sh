@@ -1,8 +1,13 @@
 set -x
-T=r4a
-timeout -s KILL 300 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/${T}_tests.log
-cat gpurun_out/${T}_tests.log
-grep -q failed gpurun_out/${T}_tests.log && exit 1
-timeout -s KILL 200 python tools/stress_preprocess.py 1500 9 2>&1 | grep -v "^frame" | tail -3
-timeout -s KILL 100 python tools/time_normalise.py 2>/dev/null | tail -1 | cut -c1-120
-timeout -s KILL 100 python tools/time_preprocess.py 2>/dev/null | tail -2
+T=r4c
+LE="timeout -s KILL 100 python tools/layer_events.py 4096 16000 3 12"
+$LE warm > /dev/null 2>&1 || exit 1
+for rep in 1 2 3 4; do
+$LE oshift >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_E2_OSHIFT=0 $LE noshift >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+done
+python - <<'P'
+import json
+for l in open('gpurun_out/r4c_layers.jsonl'):
+    d=json.loads(l); print(d['tag'], {k:round(v,3) for k,v in d['layer_ms'].items() if int(k.split(':')[0])<=4}, round(d['conv_ms'],3))
+P
