@@ -1,13 +1,11 @@
 set -x
-T=r4c
-LE="timeout -s KILL 100 python tools/layer_events.py 4096 16000 3 12"
-$LE warm > /dev/null 2>&1 || exit 1
-for rep in 1 2 3 4; do
-$LE oshift >> gpurun_out/${T}_layers.jsonl 2>/dev/null
-RISER_E2_OSHIFT=0 $LE noshift >> gpurun_out/${T}_layers.jsonl 2>/dev/null
-done
+T=r4d
+timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 python - <<'P'
 import json
-for l in open('gpurun_out/r4c_layers.jsonl'):
-    d=json.loads(l); print(d['tag'], {k:round(v,3) for k,v in d['layer_ms'].items() if int(k.split(':')[0])<=4}, round(d['conv_ms'],3))
+d=json.load(open('gpurun_out/r4d_bench.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['frac_burst'], d['e2e']['value'], d['roofline_normalise']['frac'], d['clocks'])
 P
+timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:normalise -s 3 -c 1 -o gpurun_out/${T}_norm python tools/time_normalise.py > /dev/null 2>&1
+timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout -s KILL 600 python tools/parity_sweep.py 8192 91 > gpurun_out/${T}_parity_sweep.json 2> gpurun_out/${T}_parity.err
+cut -c1-900 gpurun_out/${T}_parity_sweep.json
