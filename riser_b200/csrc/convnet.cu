@@ -3012,7 +3012,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       lp.pair = 1;
       char ntile_key[32];
       snprintf(ntile_key, sizeof ntile_key, "RISER_PAIR_NTILE_L%d", i);      // per-layer override (tuning)
-      const int wide = std::max(64, std::min(kMaxNTile, env_int(ntile_key, env_int("RISER_PAIR_NTILE", kMaxNTile))) & ~31);
+      const int wide = std::max(64, std::min(kMaxNTile, env_int(ntile_key, env_int("RISER_PAIR_NTILE", kMaxNTile))) & ~15);
       a.n_tile = std::min(wide, L.cout_p);
       a.n_tiles = (L.cout_p + a.n_tile - 1) / a.n_tile;
       a.n_last = L.cout_p - (a.n_tiles - 1) * a.n_tile;

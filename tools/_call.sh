@@ -1,11 +1,18 @@
 set -x
-T=r4d
-timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+T=r4e
+timeout -s KILL 200 env RISER_PAIR_NTILE_L7=176 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "every_layer" 2>&1 | tail -3 > gpurun_out/${T}_tests.log
+cat gpurun_out/${T}_tests.log
+grep -q passed gpurun_out/${T}_tests.log || exit 1
+grep -q failed gpurun_out/${T}_tests.log && exit 1
+LE="timeout -s KILL 100 python tools/layer_events.py 4096 16000 3 12"
+$LE warm > /dev/null 2>&1 || exit 1
+for rep in 1 2 3; do
+$LE base >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR_NTILE_L7=176 $LE l7_176 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR_NTILE_L7=176 RISER_PAIR_NTILE_L10=240 $LE l7_176_l10_240 >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+done
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/r4d_bench.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['frac_burst'], d['e2e']['value'], d['roofline_normalise']['frac'], d['clocks'])
+for l in open('gpurun_out/r4e_layers.jsonl'):
+    d=json.loads(l); print(d['tag'], {k:round(v,3) for k,v in d['layer_ms'].items() if int(k.split(':')[0]) in (6,7,10)}, round(d['conv_ms'],3))
 P
-timeout -s KILL 300 ncu --set full --import-source on --clock-control none -k regex:normalise -s 3 -c 1 -o gpurun_out/${T}_norm python tools/time_normalise.py > /dev/null 2>&1
-timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout -s KILL 600 python tools/parity_sweep.py 8192 91 > gpurun_out/${T}_parity_sweep.json 2> gpurun_out/${T}_parity.err
-cut -c1-900 gpurun_out/${T}_parity_sweep.json
