@@ -118,6 +118,7 @@ struct ConvArgs {
   int epi_sets;           // epilogue warp sets (each = 4 warps covering the TMEM lane quadrants)
   int dual;               // conv_tc_kernel, MS == 2: one MMA-issuing thread PER SUB-TILE (warp 1 and the last warp)
   int dbg_skip;           // conv_pair_kernel timing experiments (WRONG results): 1 = no weight loads, 2 = no activation loads
+  uint32_t nt_magic;      // conv_pair_kernel: floor(2^32 / n_tiles) + 1 -- item / n_tiles = umulhi(item, nt_magic) (items < 2^24); 0 = divide
   int acc_cols;           // TMEM columns per accumulator slot (n_tile rounded up to 32)
   int half_lp;            // Lp_in / 2
   int a_tx_bytes;         // bytes TMA delivers per A tile (box rows x row bytes)
@@ -2210,19 +2211,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // item -> (M super-tile, N tile), N fastest; the pair visits item = pair, pair + n_pairs_grid, ...
   // (the N tile is rotated by the super-tile index: the grid stride may be a multiple of n_tiles, and the last tile
   //  is narrower than the others -- every pair then still gets its share of both widths)
-  auto item_super = [&](int item) { return a.super0 + item / a.n_tiles; };
-  auto item_n = [&](int item) { return (item % a.n_tiles + item / a.n_tiles) % a.n_tiles; };
+  // (division by the run-time n_tiles through a multiply: the roles that walk the item list -- the MMA-issuing warp
+  //  among them -- did two divisions and two remainders, ~120 instructions, per item)
+  auto div_nt = [&](int x) {
+    if (a.n_tiles == 1) return x;
+    return a.nt_magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), a.nt_magic)) : x / a.n_tiles;
+  };
+  auto item_super = [&](int item) { return a.super0 + div_nt(item); };
+  auto item_n = [&](int item) {
+    const int q = div_nt(item), t = item - q * a.n_tiles + q;          // item % n_tiles + item / n_tiles
+    return t - div_nt(t) * a.n_tiles;
+  };
   // Activity flag of item, item + stride, ...: the NEXT item's flag is loaded while the current item is worked on
   // (a global load per item otherwise sits on the critical path of the single-thread roles).
   struct PairFlags {
     const uint8_t* flags;
     int n_tiles, super0, stride, n_items;
     uint32_t next;
+    uint32_t magic;
     __device__ __forceinline__ uint32_t load(int item) const {
-      return (flags && item < n_items) ? __ldg(flags + super0 + item / n_tiles) : 1u;
+      const int q = (n_tiles == 1) ? item : magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(item), magic)) : item / n_tiles;
+      return (flags && item < n_items) ? __ldg(flags + super0 + q) : 1u;
     }
-    __device__ __forceinline__ PairFlags(const uint8_t* f, int nt, int s0, int first, int stride_, int n)
-        : flags(f), n_tiles(nt), super0(s0), stride(stride_), n_items(n) { next = load(first); }
+    __device__ __forceinline__ PairFlags(const uint8_t* f, int nt, int s0, int first, int stride_, int n, uint32_t mg = 0)
+        : flags(f), n_tiles(nt), super0(s0), stride(stride_), n_items(n), magic(mg) { next = load(first); }
     __device__ __forceinline__ bool take(int item) {      // call once per item, in order
       const uint32_t now = next;
       next = load(item + stride);
@@ -2245,7 +2257,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
+      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items, a.nt_magic);
       for (int item = pair; item < n_items; item += n_pairs_grid) {
         if (!fl.take(item)) continue;
         const int m0 = item_super(item) * (MS * 256) + static_cast<int>(rank) * kBlockM - 1;
@@ -2321,7 +2333,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(&s.w_full, 0);
         tc_fence_after();
       }
-      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
+      PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items, a.nt_magic);
       for (int item = pair; item < n_items; item += n_pairs_grid) {
         if (!fl.take(item)) continue;
         const uint32_t d_base = tmem_base + stage * acc_stride;
@@ -2389,7 +2401,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int lo_off = (a.out_planes == 2 && !a.out_f8) ? a.cout_p : 0;
     int stage = 0, it = -1;
     uint32_t acc_phase = 0;
-    PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items);
+    PairFlags fl(a.flags, a.n_tiles, a.super0, pair, n_pairs_grid, n_items, a.nt_magic);
     for (int item = pair; item < n_items; item += n_pairs_grid) {
       if (!fl.take(item)) continue;
       ++it;
@@ -3036,6 +3048,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
       a.acc_stages = std::max(1, std::min(kMaxAccStages, kTmemCols / (a.ms * a.acc_cols)));
       a.dual = (a.ms == 2 && env_int("RISER_DUAL_ISSUE", 1)) ? 1 : 0;
       a.dbg_skip = env_int("RISER_PAIR_DBG_SKIP", 0);       // timing experiments only
+      a.nt_magic = 0;      // (set below, once n_tiles is final)
       a.resident = 0;
       size_t b_total = a.b_stages * half_b;
       const size_t w_half = static_cast<size_t>(3) * a.k_blocks * half_b;      // this CTA's half of every tap and K block
@@ -3045,6 +3058,7 @@ extern "C" int riser_plan_create(riser_plan** out, const riser_model* m, int B, 
         b_total = w_half;
       }
       a.epi_sets = 4;
+      a.nt_magic = (env_int("RISER_PAIR_MAGIC", 1) && a.n_tiles > 1) ? static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(a.n_tiles)) + 1u : 0u;
       lp.smem = fixed + a.a_stages * a_group + b_total;
       lp.rows_per_super = a.ms * 256;
     }

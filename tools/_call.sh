@@ -1,11 +1,18 @@
 set -x
-T=r4g
-CS="compute-sanitizer --error-exitcode 9"
-( timeout -s KILL 300 $CS --tool memcheck python tools/stress_preprocess.py 200 12 2>&1 | tail -4; echo rc=$? ) > gpurun_out/${T}_pre_memcheck.txt
-cat gpurun_out/${T}_pre_memcheck.txt
-( timeout -s KILL 400 $CS --tool racecheck python tools/stress_preprocess.py 120 13 2>&1 | tail -4; echo rc=$? ) > gpurun_out/${T}_pre_racecheck.txt
-cat gpurun_out/${T}_pre_racecheck.txt
-( timeout -s KILL 400 $CS --tool memcheck python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q -k "ranges or corner or edge or outlier" 2>&1 | tail -4; echo rc=$? ) > gpurun_out/${T}_pre_tests_memcheck.txt
-cat gpurun_out/${T}_pre_tests_memcheck.txt
-( timeout -s KILL 300 $CS --tool synccheck python tools/stress_preprocess.py 120 14 2>&1 | tail -4; echo rc=$? ) > gpurun_out/${T}_pre_synccheck.txt
-cat gpurun_out/${T}_pre_synccheck.txt
+T=r4h
+timeout -s KILL 200 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "every_layer" 2>&1 | tail -3 > gpurun_out/${T}_tests.log
+cat gpurun_out/${T}_tests.log
+grep -q passed gpurun_out/${T}_tests.log || exit 1
+grep -q failed gpurun_out/${T}_tests.log && exit 1
+LE="timeout -s KILL 100 python tools/layer_events.py 4096 16000 3 12"
+$LE warm > /dev/null 2>&1 || exit 1
+for rep in 1 2 3 4; do
+$LE magic >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+RISER_PAIR_MAGIC=0 $LE divide >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+done
+python - <<'P'
+import json
+for l in open('gpurun_out/r4h_layers.jsonl'):
+    d=json.loads(l); lm=d['layer_ms']; s=sum(v for k,v in lm.items() if int(k.split(':')[0])>=5)
+    print(d['tag'], {k:round(v,3) for k,v in lm.items() if int(k.split(':')[0]) >=5}, 'sum5-11', round(s,3), round(d['conv_ms'],3))
+P
