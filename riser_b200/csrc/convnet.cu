@@ -938,19 +938,22 @@ ConvKernelFn pick_conv_kernel(int ms, int planes, int wplanes, int resident, int
 // are row-shifted views of the two tiles accumulated into two column ranges of the same lane.
 //
 // Work item = 255 pooled layer-1 outputs (pair indices u0 .. u0+254; E rows 0..255 = E[u0+i],
-// O rows 0..255 = O[u0+i-1]).  Roles (22 warps):
+// O rows 0..255 = O[u0+i-1]).  Roles (24 warps):
 //   warp 0        producer: bulk copies (TMA) of the item's signal segment into a 4-stage ring
-//   warps 2..5    cvt1: signal (shared memory) -> layer-0 A rows in shared memory
+//   warps 2..7    cvt1: signal (shared memory) -> layer-0 A rows in shared memory
 //   warp 1        MMA issuer (layer 0 of item k+1 is issued before layer 1 of item k)
-//   warps 6..13   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
-//   warps 14..21  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
+//   warps 8..15   mid-epilogue: layer-0 accumulators -> max, ReLU, fp16 hi (+ lo) -> layer-1 A tiles
+//   warps 16..23  epilogue: layer-1 accumulators -> max, bias, ReLU, mask -> act_2 in HBM
 constexpr int kF2Pairs = 255;
-constexpr int kF2Threads = 704;
+#ifndef RISER_F2_CVT_WARPS
+#define RISER_F2_CVT_WARPS 6
+#endif
+constexpr int kF2Threads = 576 + 32 * RISER_F2_CVT_WARPS;     // producer + issuer + cvt1 + 8 mid-epilogue + 8 epilogue warps
 constexpr uint32_t kF2A1Tile = 264 * 64;   // 256 rows + the slack row the shifted taps of row 255 touch
 constexpr uint32_t kF2A0Tile = 256 * 64;   // per row: [E window (K=16) | O window (K=16)]
 constexpr int kF2N0 = 48;
 constexpr int kF2D0Col = 256;              // TMEM: layer-1 accumulators [0,256), layer-0 at 256 + 48*k
-constexpr int kF2CvtThreads = 128;     // four cvt1 warps (two were ~100 % busy: the stage that paced the launch)
+constexpr int kF2CvtThreads = 32 * RISER_F2_CVT_WARPS;     // six cvt1 warps: 257 rows in two passes (two warps were ~100 % busy; with four the issuer still waited on a0_full: 4 -> 6 -> 9 warps 1.04 / 1.01 / 1.00 ms on one box)
 constexpr int kF2XStages = 4;
 constexpr int kF2MaxLocalItems = 2048;   // work items per CTA whose activity flags fit the shared-memory copy
 constexpr uint32_t kF2XStage = 260 * 16;     // pairs i = -2 .. 256 (4 samples each) + pad
