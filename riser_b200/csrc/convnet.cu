@@ -1459,58 +1459,76 @@ fused01_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__
       mbar_wait_relaxed(&s.d1_full[st], (k >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + st * 128 + 2 * sub * 32;
+      // m[c] = max of the two conv positions of a pool pair (accumulator units); bias, ReLU, mask, fp16 hi + lo, stores
+      auto finish = [&](int c16, const float (&m)[16]) {
+        if (!(writable && !((RISER_DBG & 2) && a.Lp_out > 0))) return;
+        float r[16];
+        if (valid) {
 #pragma unroll
-      for (int c16 = 0; c16 < 2; ++c16) {
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bb = *reinterpret_cast<const float4*>(&s.bias[c16 * 16 + c4 * 4]);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c4 * 4 + e;
+              r[c] = fmaxf(fmaf(m[c], inv_scale, bv[e]), 0.f);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) r[c] = 0.f;
+        }
+        __half2 hv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
+        st_global_256(orow + c16 * 16, *reinterpret_cast<const uint4*>(hv), *reinterpret_cast<const uint4*>(hv + 4));
+        if (lo_off) {
+          __half2 lv[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float2 back = __half22float2(hv[c]);
+            lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
+          }
+          st_global_256(orow + lo_off + c16 * 16, *reinterpret_cast<const uint4*>(lv),
+                        *reinterpret_cast<const uint4*>(lv + 4));
+        }
+        if (a.out_f8)
+          store_f8_planes<16>(r, hv, reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c16 * 16, a.cout_p);
+      };
+      // The second half's accumulator columns are loaded while the first half is finished, and the accumulator is
+      // handed back to the MMA warp as soon as they have arrived -- before, not after, the second half's arithmetic and
+      // stores (the MMA warp was waiting on d1_empty).
+      float m0[16];
+      {
         uint32_t ve[16], vo[16];
         if (RISER_DBG & 8) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) ve[j] = vo[j] = 0u;
         } else {
-          tmem_ld_32x16(taddr + c16 * 16, ve);
-          tmem_ld_32x16(taddr + 32 + c16 * 16, vo);
+          tmem_ld_32x16(taddr, ve);
+          tmem_ld_32x16(taddr + 32, vo);
         }
         tmem_ld_wait();
-        if (c16 == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s.d1_empty[st][sub]);
-        }
-        if (writable && !((RISER_DBG & 2) && a.Lp_out > 0)) {
-          float r[16];
-          if (valid) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&s.bias[c16 * 16 + c4 * 4]);
-              const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = c4 * 4 + e;
-                r[c] = fmaxf(fmaf(fmaxf(__uint_as_float(ve[c]), __uint_as_float(vo[c])), inv_scale, bv[e]), 0.f);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) r[c] = 0.f;
-          }
-          __half2 hv[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) hv[c] = sat_half2(r[2 * c], r[2 * c + 1]);
-          st_global_256(orow + c16 * 16, *reinterpret_cast<const uint4*>(hv), *reinterpret_cast<const uint4*>(hv + 4));
-          if (lo_off) {
-            __half2 lv[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float2 back = __half22float2(hv[c]);
-              lv[c] = __floats2half2_rn(r[2 * c] - back.x, r[2 * c + 1] - back.y);
-            }
-            st_global_256(orow + lo_off + c16 * 16, *reinterpret_cast<const uint4*>(lv),
-                          *reinterpret_cast<const uint4*>(lv + 4));
-          }
-          if (a.out_f8)
-            store_f8_planes<16>(r, hv, reinterpret_cast<uint8_t*>(orow) + 2 * a.cout_p + c16 * 16, a.cout_p);
-        }
-        __syncwarp();
+        for (int j = 0; j < 16; ++j) m0[j] = fmaxf(__uint_as_float(ve[j]), __uint_as_float(vo[j]));
       }
+      uint32_t ve1[16], vo1[16];
+      if (RISER_DBG & 8) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ve1[j] = vo1[j] = 0u;
+      } else {
+        tmem_ld_32x16(taddr + 16, ve1);
+        tmem_ld_32x16(taddr + 32 + 16, vo1);
+      }
+      finish(0, m0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.d1_empty[st][sub]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) m0[j] = fmaxf(__uint_as_float(ve1[j]), __uint_as_float(vo1[j]));
+      finish(1, m0);
+      __syncwarp();
     }
   }
 
