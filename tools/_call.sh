@@ -1,13 +1,17 @@
 set -x
-T=r4m
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/${T}_tests.log
+T=r4n
+RISER_F01_QUAD=1 timeout -s KILL 200 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "every_layer" 2>&1 | tail -2 > gpurun_out/${T}_tests.log
 cat gpurun_out/${T}_tests.log
+grep -q passed gpurun_out/${T}_tests.log || exit 1
 grep -q failed gpurun_out/${T}_tests.log && exit 1
-timeout -s KILL 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+LE="timeout -s KILL 100 python tools/layer_events.py 4096 16000 3 12"
+$LE warm > /dev/null 2>&1 || exit 1
+for rep in 1 2 3 4; do
+RISER_F01_QUAD=1 $LE quad >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+$LE noquad >> gpurun_out/${T}_layers.jsonl 2>/dev/null
+done
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/r4m_bench.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['frac_burst'], d['e2e']['value'], d['roofline_normalise']['frac'], d['clocks'])
+for l in open('gpurun_out/r4n_layers.jsonl'):
+    d=json.loads(l); print(d['tag'], {k:round(v,3) for k,v in d['layer_ms'].items() if int(k.split(':')[0]) <=2}, round(d['conv_ms'],3))
 P
-timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"fused01|conv_tc|conv_eo|conv_pair" -s 10 -c 10 -o gpurun_out/${T}_conv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-du -sh gpurun_out
